@@ -1,0 +1,832 @@
+// rg_b200.cu -- kernels, host runtime and C ABI (include/rg_b200.h) of the B200-native RG hot path.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -fmad=false -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rg_b200.h"
+#include "rg_plan.hpp"
+#include "rg_device.cuh"
+#include "rg_multiply.cuh"
+
+using namespace rgdev;
+
+// Taylor orders J with a compiled kernel (the Taylor loops are fully unrolled per J).
+#ifndef RG_J_LIST
+#define RG_J_LIST(X) X(4) X(5) X(6) X(10)
+#endif
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(x)                                                                                         \
+    do {                                                                                              \
+        cudaError_t e_ = (x);                                                                         \
+        if (e_ != cudaSuccess) {                                                                      \
+            return fail((int)e_, std::string(#x) + ": " + cudaGetErrorString(e_));                   \
+        }                                                                                             \
+    } while (0)
+
+extern "C" const char* rg_last_error(void) { return g_err.c_str(); }
+extern "C" int rg_device_count(int* n) {
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) { *n = 0; return fail((int)e, cudaGetErrorString(e)); }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct Job {
+    int mode;  // 0 region (amps), 1 converge (f given), 2 rg_map x n_iter, 3 expm, 4 liouville, 5 generate_y
+    int n;
+    int sched;  // 0 sparse, 1 dense
+    int* ticket;
+    // inputs
+    const double* amps; const int* K_flat; int nK;   // mode 0 (K_flat: j*M + centred mode)
+    const double* f_in;                               // [n][vecjl] wrapped layout
+    const int* k0;                                    // may be null
+    int n_iter;
+    const double* y0; const double* y1; const double* y2; const double* y3;  // mode 3/4 (wrapped layout)
+    const double* Omega_nu;                           // [M] centred (mode 3/4/5)
+    double step; int ct;
+    // outputs
+    int* conv; int* count; int* err;
+    double* f_out; double* y0_out; double* y1_out; double* y2_out; double* y3_out;
+    long long* n_liou; long long* n_lie; long long* n_maps;
+    double* ws_base;
+};
+
+__device__ __forceinline__ void load_wrapped(const DevPlan& P, const double* __restrict__ src, double* __restrict__ dst) {
+    for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
+        const int j = i / P.M, c = i - j * P.M;
+        dst[i] = src[j * P.M + P.c2w[c]];
+    }
+}
+__device__ __forceinline__ void store_wrapped(const DevPlan& P, const double* __restrict__ src, double* __restrict__ dst) {
+    for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
+        const int j = i / P.M, c = i - j * P.M;
+        dst[j * P.M + P.c2w[c]] = src[i];
+    }
+}
+
+template <int J>
+__global__ void __launch_bounds__(512, 1) rg_kernel(const int slot, const __grid_constant__ Tables T, const __grid_constant__ Job job) {
+    Ctx c;
+    c.slot = slot;
+    c.sidx = job.sched;
+    const DevPlan& P = RG_PLAN(c);
+    const Smem sm = smem_view(P, RG_SCHED(c));
+    int* sh_item = reinterpret_cast<int*>(sm.red + 64);
+    c.ws = job.ws_base + (size_t)blockIdx.x * WS_COUNT * P.vecjl;
+    c.Omega_nu = T.Omega_nu;
+    // zero all records once (pads and the all-zero record stay zero for the life of the CTA)
+    {
+        const int nd2 = (P.M + 1 + RG_SCHED(c).n_support) * P.rec_units;
+        for (int i = threadIdx.x; i < nd2; i += blockDim.x) sm.G[i] = make_double2(0.0, 0.0);
+    }
+    double* fa = c.ws + (size_t)WS_FA * P.vecjl;
+    const int M = P.M, c0 = (M - 1) / 2;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) *sh_item = atomicAdd(job.ticket, 1);
+        __syncthreads();
+        const int item = *sh_item;
+        if (item >= job.n) break;
+        c.n_liou = 0; c.n_lie = 0;
+        long long n_maps = 0;
+        double* f = fa;
+        const int k0 = job.k0 ? job.k0[item] : 0;
+        if (job.mode == 0) {
+            // generate_1Hamiltonian(amps, symmetric=True)  RG.py:255-264
+            for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) f[i] = 0.0;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int q = 0; q < job.nK; ++q) f[job.K_flat[q]] = job.amps[(size_t)item * job.nK + q];
+                f[2 * M + c0] = 0.5;
+            }
+            __syncthreads();
+            sym_and_norms(c, f, true);
+        } else {
+            load_wrapped(P, job.f_in + (size_t)item * P.vecjl, f);
+            __syncthreads();
+        }
+        if (job.mode == 0 || job.mode == 1) {
+            // RG.converge  RG.py:278-290
+            double2 nn = sym_and_norms(c, f, false);
+            double ni = nn.y;
+            int k = 0, err = 0;
+            bool overflow = false;
+            while (P.tol_max > ni && ni > P.tol_min) {
+                if (k0 + k >= T.n_tab) { overflow = true; break; }
+                f = rg_map_dev<J>(c, f, T, k0 + k, err, ni);
+                ++k; ++n_maps;
+            }
+            if (threadIdx.x == 0) {
+                const bool cv = ni < P.tol_min;
+                job.conv[item] = (cv && !overflow) ? 1 : 0;
+                job.count[item] = (cv && !overflow) ? -k : k;
+                if (overflow) job.err[item] = RG_ERR_TABLE_EXHAUSTED;
+                else if (!cv) job.err[item] = err;
+                else if (job.mode == 0) job.err[item] = 0;
+            }
+        } else if (job.mode == 2) {
+            int err = 0; double ni;
+            for (int k = 0; k < job.n_iter; ++k) {
+                if (k0 + k >= T.n_tab) { err = RG_ERR_TABLE_EXHAUSTED; break; }
+                f = rg_map_dev<J>(c, f, T, k0 + k, err, ni);
+                ++n_maps;
+            }
+            __syncthreads();
+            store_wrapped(P, f, job.f_out + (size_t)item * P.vecjl);
+            if (threadIdx.x == 0) job.err[item] = err;
+        } else if (job.mode == 3 || job.mode == 4) {
+            // caller-supplied y (wrapped) -> WS_Y1..3
+            c.Omega_nu = job.Omega_nu;
+            load_wrapped(P, job.y1 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y1 * P.vecjl);
+            load_wrapped(P, job.y2 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y2 * P.vecjl);
+            if (job.mode == 3) load_wrapped(P, job.y3 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y3 * P.vecjl);
+            __syncthreads();
+            const double a = job.y0[item];
+            if (job.mode == 3) {
+                int err = job.err[item];
+                if (job.ct == 0) err = expm_onestep<J>(c, f, a, job.step);
+                else if (job.ct == 1) err = expm_adapt<J>(c, f, a, job.step, err);
+                else err = expm_multiply<J>(c, f, a);
+                __syncthreads();
+                store_wrapped(P, f, job.f_out + (size_t)item * P.vecjl);
+                if (threadIdx.x == 0) job.err[item] = err;
+            } else {
+                // RG.liouville  RG.py:115-117
+                double* dst = c.ws + (size_t)WS_T0 * P.vecjl;
+                build_Y(c, 1.0, 1.0, false);
+                liouville_apply<J>(c, f, dst, a, false);
+                __syncthreads();
+                store_wrapped(P, dst, job.f_out + (size_t)item * P.vecjl);
+            }
+        } else if (job.mode == 5) {
+            c.Omega_nu = job.Omega_nu;
+            const double a = generate_y(c, f);
+            __syncthreads();
+            store_wrapped(P, c.ws + (size_t)WS_Y1 * P.vecjl, job.y1_out + (size_t)item * P.vecjl);
+            store_wrapped(P, c.ws + (size_t)WS_Y2 * P.vecjl, job.y2_out + (size_t)item * P.vecjl);
+            store_wrapped(P, c.ws + (size_t)WS_Y3 * P.vecjl, job.y3_out + (size_t)item * P.vecjl);
+            if (threadIdx.x == 0) job.y0_out[item] = a;
+        }
+        if (threadIdx.x == 0 && job.n_liou) {
+            job.n_liou[item] = c.n_liou; job.n_lie[item] = c.n_lie; job.n_maps[item] = n_maps;
+        }
+    }
+}
+
+// ---- small HBM-bound batched operators (one CTA per Hamiltonian, coalesced over the mode index) ----
+// RG.norm / norm_int / I^- norm (RG.py:92-97,244-247,217-218).  Wrapped layout in, one double out.
+__global__ void __launch_bounds__(256) norm_kernel(const DevPlan P, int n, const double* __restrict__ f, int which, double* __restrict__ out) {
+    __shared__ double red[64];
+    const int type = P.norm_choice;
+    for (int item = blockIdx.x; item < n; item += gridDim.x) {
+        const double* fi = f + (size_t)item * P.vecjl;
+        double p = 0.0, q = 0.0;
+        for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
+            const int j = i / P.M, cidx = i - j * P.M;
+            const int w = P.c2w[cidx];
+            const double v = fi[j * P.M + w];
+            bool use = true;
+            if (which == RG_WHICH_NORM_INT) use = (w != 0);
+            else if (which == RG_WHICH_NORM_IMINUS) use = (P.mask[cidx] >> j) & 1u;
+            if (use) norm_acc(type, p, v, type == 3 ? P.normw[cidx] : 1.0);
+        }
+        double2 r = block_reduce2(red, type, p, q);
+        if (threadIdx.x == 0) out[item] = r.x;
+    }
+}
+// RG.sym (RG.py:249-253)
+__global__ void __launch_bounds__(256) sym_kernel(const DevPlan P, int n, const double* __restrict__ f, double* __restrict__ out) {
+    for (int item = blockIdx.x; item < n; item += gridDim.x) {
+        const double* fi = f + (size_t)item * P.vecjl;
+        double* oi = out + (size_t)item * P.vecjl;
+        for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
+            const int j = i / P.M, cidx = i - j * P.M;
+            const int w = P.c2w[cidx], wm = P.c2w[P.M - 1 - cidx];
+            double v = (fi[j * P.M + w] + fi[j * P.M + wm]) / 2;
+            if (j == 0 && w == 0) v = 0.0;
+            oi[j * P.M + w] = v;
+        }
+    }
+}
+// head of RG.rg_map (RG.py:210-216)
+__global__ void __launch_bounds__(256) reindex_kernel(const DevPlan P, const Tables T, int n, const double* __restrict__ f, const int* __restrict__ k0, double* __restrict__ out) {
+    __shared__ double ren[32];
+    for (int item = blockIdx.x; item < n; item += gridDim.x) {
+        const double* fi = f + (size_t)item * P.vecjl;
+        double* oi = out + (size_t)item * P.vecjl;
+        const int k = k0 ? k0[item] : 0;
+        const double f2 = fi[2 * P.M];
+        const double base = 2 * T.nrm[k] / P.eigenvalue * f2;
+        __syncthreads();
+        if (threadIdx.x <= P.J) ren[threadIdx.x] = pow(base, (double)(2 - (int)threadIdx.x)) / (2 * f2);
+        __syncthreads();
+        for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
+            const int j = i / P.M, cidx = i - j * P.M;
+            const int s = P.reidx[cidx];
+            oi[j * P.M + P.c2w[cidx]] = (s >= 0 ? fi[j * P.M + P.c2w[s]] : 0.0) * ren[j];
+        }
+    }
+}
+// RG.conv_product (RG.py:102-106) for arbitrary operands: operands staged in shared memory (centred),
+// one thread per output element.  Not on the fused path (the Lie series uses conv_all).
+__global__ void __launch_bounds__(256) conv_kernel(const DevPlan P, int n, const double* __restrict__ f1, const double* __restrict__ f2, double* __restrict__ out) {
+    extern __shared__ double2 sm2[];
+    double* A = reinterpret_cast<double*>(sm2);
+    double* B = A + P.vecjl;
+    const int M = P.M, L = P.L, n1 = P.n1;
+    for (int item = blockIdx.x; item < n; item += gridDim.x) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
+            const int j = i / M, cidx = i - j * M;
+            A[i] = f1[(size_t)item * P.vecjl + j * M + P.c2w[cidx]];
+            B[i] = f2[(size_t)item * P.vecjl + j * M + P.c2w[cidx]];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
+            const int j = i / M, cidx = i - j * M;
+            int v[3] = {0, 0, 0};
+            { int r = cidx; for (int d = P.dim - 1; d >= 0; --d) { v[d] = r % n1; r /= n1; } }
+            double acc = 0.0;
+            for (int j1 = 0; j1 <= j; ++j1) {
+                const double* Aj = A + j1 * M; const double* Bj = B + (j - j1) * M;
+                if (P.dim == 2) {
+                    for (int a1 = max(0, v[0] - L); a1 <= min(n1 - 1, v[0] + L); ++a1) {
+                        const int a2 = v[0] + L - a1;
+                        for (int b1 = max(0, v[1] - L); b1 <= min(n1 - 1, v[1] + L); ++b1)
+                            acc = fma(Aj[a1 * n1 + b1], Bj[a2 * n1 + (v[1] + L - b1)], acc);
+                    }
+                } else if (P.dim == 3) {
+                    for (int a1 = max(0, v[0] - L); a1 <= min(n1 - 1, v[0] + L); ++a1)
+                        for (int b1 = max(0, v[1] - L); b1 <= min(n1 - 1, v[1] + L); ++b1)
+                            for (int c1 = max(0, v[2] - L); c1 <= min(n1 - 1, v[2] + L); ++c1)
+                                acc = fma(Aj[(a1 * n1 + b1) * n1 + c1],
+                                          Bj[((v[0] + L - a1) * n1 + (v[1] + L - b1)) * n1 + (v[2] + L - c1)], acc);
+                } else {
+                    for (int a1 = max(0, v[0] - L); a1 <= min(n1 - 1, v[0] + L); ++a1) acc = fma(Aj[a1], Bj[v[0] + L - a1], acc);
+                }
+            }
+            out[(size_t)item * P.vecjl + j * M + P.c2w[cidx]] = acc;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host runtime
+struct DevSched {
+    int* lane_out = nullptr; uint32_t* lane_coord = nullptr; int4* pieces = nullptr; uint2* entries = nullptr; int* supp_rec = nullptr;
+};
+
+struct rg_plan {
+    rgplan::Geometry g;
+    rgplan::Schedule hs[2];
+    DevSched ds[2];
+    DevPlan dp;
+    int device = 0;
+    int slot = -1;  // index into the constant-memory plan table
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int threads = 0, sm_count = 0;
+    size_t smem[2] = {0, 0};
+    int ctas_per_sm[2] = {0, 0};
+    int grid_max[2] = {0, 0};
+    double* ws = nullptr; size_t ws_ctas = 0;
+    int* ticket = nullptr;
+    std::vector<void*> owned;  // device allocations
+    std::vector<int> w2c;      // wrapped -> centred
+    void* kernel = nullptr;
+    // scratch for staging
+    std::vector<void*> scratch;
+};
+
+struct rg_tables {
+    rg_plan* plan;
+    Tables t;
+    double* d_nrm = nullptr; double* d_onu = nullptr;
+};
+
+static bool g_slot_used[RG_MAX_PLANS] = {false};
+static int alloc_slot() { for (int i = 0; i < RG_MAX_PLANS; ++i) if (!g_slot_used[i]) { g_slot_used[i] = true; return i; } return -1; }
+
+template <typename T>
+static int dev_upload(rg_plan* p, const T* host, size_t n, T** out) {
+    T* d = nullptr;
+    CU(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) CU(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    p->owned.push_back(d);
+    *out = d;
+    return 0;
+}
+
+typedef void (*kern_t)(const int, const Tables, const Job);
+static kern_t pick_kernel(int J) {
+    switch (J) {
+#define RG_CASE(j) case j: return rg_kernel<j>;
+        RG_J_LIST(RG_CASE)
+#undef RG_CASE
+        default: return nullptr;
+    }
+}
+
+static size_t smem_bytes(const rg_plan* p, int s) {
+    const rgplan::Geometry& g = p->g;
+    size_t b = (size_t)(g.M + 1 + p->hs[s].n_support) * g.rec_units * 16;
+    b += (size_t)g.M * g.JP * 8;
+    b += 64 * 8 + 16;
+    return b;
+}
+
+static std::vector<uint16_t> masks_from_iminus(const rgplan::Geometry& g, const uint8_t* iminus_wrapped) {
+    std::vector<uint16_t> mask(g.M, 0);
+    for (int c = 0; c < g.M; ++c) {
+        int w = g.wrapped_of_centred(c);
+        uint16_t m = 0;
+        for (int j = 0; j <= g.J; ++j) if (iminus_wrapped[(size_t)j * g.M + w]) m |= (uint16_t)(1u << j);
+        mask[c] = m;
+    }
+    return mask;
+}
+
+extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
+    if (!prm || !out) return fail(-1, "null argument");
+    if (prm->dim < 1 || prm->dim > 3) return fail(-2, "dim must be 1, 2 or 3");
+    if (prm->J < 2 || prm->J > 15) return fail(-2, "J must be in 2..15");
+    if (prm->L < 1 || prm->L > 60) return fail(-2, "L must be in 1..60");
+    if (!pick_kernel(prm->J)) return fail(-3, "no kernel compiled for J=" + std::to_string(prm->J) + " (rebuild with RG_B200_J_LIST)");
+    if (prm->ct < 0 || prm->ct > 2) return fail(-2, "unknown canonical transformation");
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (prm->device < 0 || prm->device >= ndev) return fail(-4, "no such CUDA device");
+    CU(cudaSetDevice(prm->device));
+    rg_plan* p = new rg_plan();
+    p->device = prm->device;
+    p->g.init(prm->dim, prm->L, prm->J);
+    const rgplan::Geometry& g = p->g;
+    std::vector<uint16_t> mask = masks_from_iminus(g, prm->iminus);
+    p->hs[0] = rgplan::make_schedule(g, mask, false);
+    p->hs[1] = rgplan::make_schedule(g, mask, true);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, p->device));
+    p->sm_count = prop.multiProcessorCount;
+    p->threads = p->hs[0].n_warps * 32;
+    if (p->threads > 512) { delete p; return fail(-5, "(2L+1)^dim > 512 modes: one CTA cannot own a Hamiltonian of this size yet"); }
+    DevPlan& dp = p->dp;
+    memset(&dp, 0, sizeof(dp));
+    dp.dim = g.dim; dp.L = g.L; dp.J = g.J; dp.JP = g.JP; dp.n1 = g.n1; dp.M = g.M; dp.vecjl = g.vecjl;
+    dp.off2 = g.off2; dp.rec_units = g.rec_units;
+    dp.idx_y1J = (g.J & 1) ? g.J : g.off2 + g.JP;
+    dp.stride0 = g.stride[0]; dp.stride1 = g.stride[1]; dp.stride2 = g.stride[2];
+    dp.norm_choice = prm->norm_choice; dp.norm_analytic = prm->norm_analytic;
+    dp.tol_min = prm->tol_min; dp.tol_max = prm->tol_max; dp.max_lie = prm->max_lie; dp.ct = prm->ct;
+    dp.min_step = prm->min_step; dp.abs_tol = prm->abs_tol; dp.rel_tol = prm->rel_tol; dp.eigenvalue = prm->eigenvalue;
+    dp.max_series = prm->max_series > 0 ? prm->max_series : 100000;
+    // centred tables
+    std::vector<double> om0(g.M), normw(g.M);
+    std::vector<int> reidx(g.M), c2w(g.M);
+    p->w2c.resize(g.M);
+    for (int c = 0; c < g.M; ++c) {
+        int w = g.wrapped_of_centred(c);
+        c2w[c] = w; p->w2c[w] = c;
+    }
+    for (int c = 0; c < g.M; ++c) {
+        int w = c2w[c];
+        om0[c] = prm->omega0_nu[w];
+        int src = prm->reidx[w];
+        reidx[c] = src >= 0 ? p->w2c[src] : -1;
+        int v[4]; g.coords(c, v);
+        int l1 = 0; for (int d = 0; d < g.dim; ++d) l1 += std::abs(v[d] - g.L);
+        normw[c] = std::exp(prm->norm_analytic * (double)l1);
+    }
+    int rc;
+    double* d_om0; uint16_t* d_mask; int* d_reidx; double* d_normw; int* d_c2w; double* d_theta;
+    if ((rc = dev_upload(p, om0.data(), om0.size(), &d_om0))) return rc;
+    if ((rc = dev_upload(p, mask.data(), mask.size(), &d_mask))) return rc;
+    if ((rc = dev_upload(p, reidx.data(), reidx.size(), &d_reidx))) return rc;
+    if ((rc = dev_upload(p, normw.data(), normw.size(), &d_normw))) return rc;
+    if ((rc = dev_upload(p, c2w.data(), c2w.size(), &d_c2w))) return rc;
+    if ((rc = dev_upload(p, prm->theta, (size_t)prm->n_theta, &d_theta))) return rc;
+    dp.omega0_nu = d_om0; dp.mask = d_mask; dp.reidx = d_reidx; dp.normw = d_normw; dp.c2w = d_c2w;
+    dp.theta = d_theta; dp.n_theta = prm->n_theta;
+    for (int s = 0; s < 2; ++s) {
+        const rgplan::Schedule& hs = p->hs[s];
+        DevSched& ds = p->ds[s];
+        if ((rc = dev_upload(p, hs.lane_out.data(), hs.lane_out.size(), &ds.lane_out))) return rc;
+        if ((rc = dev_upload(p, hs.lane_coord.data(), hs.lane_coord.size(), &ds.lane_coord))) return rc;
+        if ((rc = dev_upload(p, reinterpret_cast<const int4*>(hs.pieces.data()), hs.pieces.size(), &ds.pieces))) return rc;
+        if ((rc = dev_upload(p, reinterpret_cast<const uint2*>(hs.entries.data()), hs.entries.size() / 2, &ds.entries))) return rc;
+        if ((rc = dev_upload(p, hs.supp_rec.data(), hs.supp_rec.size(), &ds.supp_rec))) return rc;
+        dp.sched[s].n_warps = hs.n_warps; dp.sched[s].n_support = hs.n_support;
+        dp.sched[s].lane_out = ds.lane_out; dp.sched[s].lane_coord = ds.lane_coord; dp.sched[s].pieces = ds.pieces;
+        dp.sched[s].entries = ds.entries; dp.sched[s].supp_rec = ds.supp_rec;
+    }
+    // the dense schedule marks every Taylor level (incl. y1[J]) as present: jm = JP+1 is written into its
+    // entries by the planner through jm[] = JP; bump here so taylor<> runs the j1 = J block
+    {
+        std::vector<uint32_t> e = p->hs[1].entries;
+        for (size_t i = 1; i < e.size(); i += 2) e[i] = (e[i] & ~0xffu) | (uint32_t)(g.JP + 1);
+        CU(cudaMemcpy(p->ds[1].entries, e.data(), e.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    p->kernel = (void*)pick_kernel(g.J);
+    for (int s = 0; s < 2; ++s) {
+        p->smem[s] = smem_bytes(p, s);
+        if (p->smem[s] > (size_t)prop.sharedMemPerBlockOptin) {
+            if (s == 0) { rg_plan_destroy(p); return fail(-5, "Hamiltonian too large for one CTA's shared memory (" + std::to_string(p->smem[s]) + " B)"); }
+            p->ctas_per_sm[s] = 0; p->grid_max[s] = 0;
+            continue;
+        }
+    }
+    size_t smax = std::max(p->smem[0], p->smem[1] <= (size_t)prop.sharedMemPerBlockOptin ? p->smem[1] : 0);
+    CU(cudaFuncSetAttribute(p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smax));
+    for (int s = 0; s < 2; ++s) {
+        if (p->smem[s] > (size_t)prop.sharedMemPerBlockOptin) continue;
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, p->kernel, p->threads, p->smem[s]));
+        if (nb < 1) { rg_plan_destroy(p); return fail(-6, "kernel does not fit on an SM"); }
+        p->ctas_per_sm[s] = nb;
+        p->grid_max[s] = nb * p->sm_count;
+    }
+    p->slot = alloc_slot();
+    if (p->slot < 0) { rg_plan_destroy(p); return fail(-8, "too many live plans (max " + std::to_string(RG_MAX_PLANS) + " per process)"); }
+    CU(cudaMemcpyToSymbol(c_plan, &p->dp, sizeof(DevPlan), sizeof(DevPlan) * (size_t)p->slot));
+    p->ws_ctas = (size_t)std::max(p->grid_max[0], p->grid_max[1]);
+    CU(cudaMalloc(&p->ws, p->ws_ctas * WS_COUNT * g.vecjl * sizeof(double)));
+    CU(cudaMemset(p->ws, 0, p->ws_ctas * WS_COUNT * g.vecjl * sizeof(double)));
+    CU(cudaMalloc(&p->ticket, sizeof(int)));
+    CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&p->ev0));
+    CU(cudaEventCreate(&p->ev1));
+    // conv_kernel needs 2*vecjl doubles of dynamic shared memory
+    if ((size_t)2 * g.vecjl * 8 <= (size_t)prop.sharedMemPerBlockOptin)
+        CU(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * g.vecjl * 8));
+    *out = p;
+    return 0;
+}
+
+extern "C" int rg_plan_destroy(rg_plan* p) {
+    if (!p) return 0;
+    cudaSetDevice(p->device);
+    for (void* d : p->owned) cudaFree(d);
+    if (p->ws) cudaFree(p->ws);
+    if (p->ticket) cudaFree(p->ticket);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->slot >= 0) g_slot_used[p->slot] = false;
+    delete p;
+    return 0;
+}
+
+extern "C" int rg_plan_info(const rg_plan* p, int32_t* threads, int32_t* smem, int32_t* ctas_per_sm, int32_t* n_support,
+                            int64_t* fma_useful, int64_t* fma_executed) {
+    if (!p) return fail(-1, "null plan");
+    if (threads) *threads = p->threads;
+    if (smem) *smem = (int32_t)p->smem[0];
+    if (ctas_per_sm) *ctas_per_sm = p->ctas_per_sm[0];
+    if (n_support) *n_support = p->hs[0].n_support;
+    if (fma_useful) *fma_useful = p->hs[0].fma_useful;
+    if (fma_executed) *fma_executed = p->hs[0].fma_executed;
+    return 0;
+}
+
+extern "C" int rg_tables_create(rg_plan* p, int32_t n_tab, const double* nrm_tab, const double* Omega_nu_tab, rg_tables** out) {
+    if (!p || !nrm_tab || !Omega_nu_tab || !out || n_tab < 1) return fail(-1, "bad argument");
+    CU(cudaSetDevice(p->device));
+    rg_tables* t = new rg_tables();
+    t->plan = p;
+    const int M = p->g.M;
+    std::vector<double> onu((size_t)(n_tab + 1) * M);
+    for (int k = 0; k <= n_tab; ++k)
+        for (int c = 0; c < M; ++c) onu[(size_t)k * M + c] = Omega_nu_tab[(size_t)k * M + p->g.wrapped_of_centred(c)];
+    CU(cudaMalloc(&t->d_nrm, sizeof(double) * n_tab));
+    CU(cudaMalloc(&t->d_onu, sizeof(double) * onu.size()));
+    CU(cudaMemcpy(t->d_nrm, nrm_tab, sizeof(double) * n_tab, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(t->d_onu, onu.data(), sizeof(double) * onu.size(), cudaMemcpyHostToDevice));
+    t->t.n_tab = n_tab; t->t.nrm = t->d_nrm; t->t.Omega_nu = t->d_onu;
+    *out = t;
+    return 0;
+}
+extern "C" int rg_tables_destroy(rg_tables* t) {
+    if (!t) return 0;
+    cudaSetDevice(t->plan->device);
+    cudaFree(t->d_nrm); cudaFree(t->d_onu);
+    delete t;
+    return 0;
+}
+
+// ---- staging: accept host or device pointers
+static bool is_device_ptr(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes a;
+    cudaError_t e = cudaPointerGetAttributes(&a, p);
+    if (e != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+struct Stage {
+    rg_plan* p;
+    std::vector<void*> tmp;
+    struct Back { void* host; void* dev; size_t bytes; };
+    std::vector<Back> backs;
+    explicit Stage(rg_plan* p_) : p(p_) {}
+    ~Stage() { for (void* d : tmp) cudaFree(d); }
+    // input: returns device pointer holding `bytes` of src
+    int in(const void* src, size_t bytes, const void** out) {
+        if (!src) { *out = nullptr; return 0; }
+        if (is_device_ptr(src)) { *out = src; return 0; }
+        void* d = nullptr;
+        CU(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
+        tmp.push_back(d);
+        CU(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, p->stream));
+        *out = d;
+        return 0;
+    }
+    // output (optionally initialised from the host buffer: in/out arrays)
+    int outp(void* dst, size_t bytes, void** out, bool copy_in = false) {
+        if (!dst) { *out = nullptr; return 0; }
+        if (is_device_ptr(dst)) { *out = dst; return 0; }
+        void* d = nullptr;
+        CU(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
+        tmp.push_back(d);
+        if (copy_in) CU(cudaMemcpyAsync(d, dst, bytes, cudaMemcpyHostToDevice, p->stream));
+        else CU(cudaMemsetAsync(d, 0, bytes, p->stream));
+        backs.push_back(Back{dst, d, bytes});
+        *out = d;
+        return 0;
+    }
+    int finish() {
+        for (auto& b : backs) CU(cudaMemcpyAsync(b.host, b.dev, b.bytes, cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        return 0;
+    }
+};
+
+static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, Stage& st) {
+    const int s = job.sched;
+    if (p->grid_max[s] < 1) return fail(-5, "this schedule does not fit in shared memory for the plan's (L, J)");
+    const rgplan::Geometry& g = p->g;
+    long long* d_cnt = nullptr;
+    if (stats) {
+        CU(cudaMalloc(&d_cnt, sizeof(long long) * 3 * (size_t)std::max(job.n, 1)));
+        st.tmp.push_back(d_cnt);
+        CU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 3 * (size_t)std::max(job.n, 1), p->stream));
+        job.n_liou = d_cnt; job.n_lie = d_cnt + job.n; job.n_maps = d_cnt + 2 * (size_t)job.n;
+    }
+    CU(cudaMemsetAsync(p->ticket, 0, sizeof(int), p->stream));
+    job.ticket = p->ticket;
+    job.ws_base = p->ws;
+    const int grid = std::max(1, std::min(job.n, p->grid_max[s]));
+    kern_t k = (kern_t)p->kernel;
+    CU(cudaEventRecord(p->ev0, p->stream));
+    k<<<grid, p->threads, p->smem[s], p->stream>>>(p->slot, T, job);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(p->ev1, p->stream));
+    if (stats) {
+        std::vector<long long> h(3 * (size_t)std::max(job.n, 1));
+        CU(cudaMemcpyAsync(h.data(), d_cnt, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, p->stream));
+        CU(cudaStreamSynchronize(p->stream));
+        memset(stats, 0, sizeof(*stats));
+        for (int i = 0; i < job.n; ++i) { stats->liouville += h[i]; stats->lie_steps += h[job.n + i]; stats->rg_maps += h[2 * (size_t)job.n + i]; }
+        stats->conv_fma_executed = stats->liouville * p->hs[s].fma_executed;
+        stats->conv_fma_useful = stats->liouville * p->hs[s].fma_useful;
+        CU(cudaEventElapsedTime(&stats->kernel_ms, p->ev0, p->ev1));
+        stats->launches = 1;
+    }
+    (void)g;
+    return 0;
+}
+
+static Tables null_tables() { Tables t; t.n_tab = 0; t.nrm = nullptr; t.Omega_nu = nullptr; return t; }
+
+extern "C" int rg_region(rg_plan* p, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
+                         int32_t* conv, int32_t* count, int32_t* err, rg_stats* stats) {
+    if (!p || !tab || n < 0 || !amps || !K_flat || nK < 1 || !conv || !count || !err) return fail(-1, "bad argument");
+    if (p->dp.ct == RG_CT_MULTIPLY && !RG_HAVE_MULTIPLY) return fail(-7, "expm_multiply not available in this build");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    Job job; memset(&job, 0, sizeof(job));
+    job.mode = 0; job.n = n; job.sched = 0; job.nK = nK;
+    // K_flat arrives as flat wrapped indices j*M + w; convert to centred
+    std::vector<int> kf(nK);
+    for (int q = 0; q < nK; ++q) { int j = K_flat[q] / p->g.M, w = K_flat[q] % p->g.M; kf[q] = j * p->g.M + p->w2c[w]; }
+    int rc;
+    const void* d;
+    int* d_kf = nullptr;
+    CU(cudaMalloc(&d_kf, sizeof(int) * nK)); st.tmp.push_back(d_kf);
+    CU(cudaMemcpyAsync(d_kf, kf.data(), sizeof(int) * nK, cudaMemcpyHostToDevice, p->stream));
+    job.K_flat = d_kf;
+    if ((rc = st.in(amps, sizeof(double) * (size_t)n * nK, &d))) return rc; job.amps = (const double*)d;
+    void* o;
+    if ((rc = st.outp(conv, sizeof(int) * (size_t)n, &o))) return rc; job.conv = (int*)o;
+    if ((rc = st.outp(count, sizeof(int) * (size_t)n, &o))) return rc; job.count = (int*)o;
+    if ((rc = st.outp(err, sizeof(int) * (size_t)n, &o))) return rc; job.err = (int*)o;
+    if ((rc = launch_job(p, tab->t, job, stats, st))) return rc;
+    return st.finish();
+}
+
+extern "C" int rg_converge(rg_plan* p, const rg_tables* tab, int32_t n, const double* f, const int32_t* k0,
+                           int32_t* conv, int32_t* count, int32_t* err_io, rg_stats* stats) {
+    if (!p || !tab || n < 0 || !f || !conv || !count || !err_io) return fail(-1, "bad argument");
+    if (p->dp.ct == RG_CT_MULTIPLY && !RG_HAVE_MULTIPLY) return fail(-7, "expm_multiply not available in this build");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    Job job; memset(&job, 0, sizeof(job));
+    job.mode = 1; job.n = n; job.sched = 0;
+    int rc; const void* d; void* o;
+    if ((rc = st.in(f, sizeof(double) * (size_t)n * p->g.vecjl, &d))) return rc; job.f_in = (const double*)d;
+    if ((rc = st.in(k0, sizeof(int) * (size_t)n, &d))) return rc; job.k0 = (const int*)d;
+    if ((rc = st.outp(conv, sizeof(int) * (size_t)n, &o))) return rc; job.conv = (int*)o;
+    if ((rc = st.outp(count, sizeof(int) * (size_t)n, &o))) return rc; job.count = (int*)o;
+    if ((rc = st.outp(err_io, sizeof(int) * (size_t)n, &o, true))) return rc; job.err = (int*)o;
+    if ((rc = launch_job(p, tab->t, job, stats, st))) return rc;
+    return st.finish();
+}
+
+extern "C" int rg_map(rg_plan* p, const rg_tables* tab, int32_t n, const double* f, const int32_t* k0, int32_t n_iter,
+                      double* f_out, int32_t* err, rg_stats* stats) {
+    if (!p || !tab || n < 0 || !f || !f_out || !err || n_iter < 0) return fail(-1, "bad argument");
+    if (p->dp.ct == RG_CT_MULTIPLY && !RG_HAVE_MULTIPLY) return fail(-7, "expm_multiply not available in this build");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    Job job; memset(&job, 0, sizeof(job));
+    job.mode = 2; job.n = n; job.sched = 0; job.n_iter = n_iter;
+    int rc; const void* d; void* o;
+    if ((rc = st.in(f, sizeof(double) * (size_t)n * p->g.vecjl, &d))) return rc; job.f_in = (const double*)d;
+    if ((rc = st.in(k0, sizeof(int) * (size_t)n, &d))) return rc; job.k0 = (const int*)d;
+    if ((rc = st.outp(f_out, sizeof(double) * (size_t)n * p->g.vecjl, &o))) return rc; job.f_out = (double*)o;
+    if ((rc = st.outp(err, sizeof(int) * (size_t)n, &o))) return rc; job.err = (int*)o;
+    if ((rc = launch_job(p, tab->t, job, stats, st))) return rc;
+    return st.finish();
+}
+
+// Omega_nu arrives in wrapped order on the host or device; the kernels want it centred on the device
+static int stage_Omega_nu(rg_plan* p, Stage& st, const double* Omega_nu, const double** out) {
+    const int M = p->g.M;
+    std::vector<double> h(M), c(M);
+    if (is_device_ptr(Omega_nu)) CU(cudaMemcpy(h.data(), Omega_nu, sizeof(double) * M, cudaMemcpyDeviceToHost));
+    else memcpy(h.data(), Omega_nu, sizeof(double) * M);
+    for (int i = 0; i < M; ++i) c[i] = h[p->g.wrapped_of_centred(i)];
+    double* d = nullptr;
+    CU(cudaMalloc(&d, sizeof(double) * M)); st.tmp.push_back(d);
+    CU(cudaMemcpy(d, c.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
+    *out = d;
+    return 0;
+}
+
+extern "C" int rg_expm(rg_plan* p, int32_t ct, int32_t n, const double* f, const double* y0, const double* y1,
+                       const double* y2, const double* y3, const double* Omega_nu, double step, double* f_out,
+                       int32_t* err_io, rg_stats* stats) {
+    if (!p || n < 0 || !f || !y0 || !y1 || !y2 || !y3 || !Omega_nu || !f_out || !err_io) return fail(-1, "bad argument");
+    if (ct < 0 || ct > 2) return fail(-2, "unknown canonical transformation");
+    if (ct == RG_CT_MULTIPLY && !RG_HAVE_MULTIPLY) return fail(-7, "expm_multiply not available in this build");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    Job job; memset(&job, 0, sizeof(job));
+    job.mode = 3; job.n = n; job.sched = 1; job.ct = ct; job.step = step;
+    const size_t vb = sizeof(double) * (size_t)n * p->g.vecjl;
+    int rc; const void* d; void* o;
+    if ((rc = st.in(f, vb, &d))) return rc; job.f_in = (const double*)d;
+    if ((rc = st.in(y0, sizeof(double) * (size_t)n, &d))) return rc; job.y0 = (const double*)d;
+    if ((rc = st.in(y1, vb, &d))) return rc; job.y1 = (const double*)d;
+    if ((rc = st.in(y2, vb, &d))) return rc; job.y2 = (const double*)d;
+    if ((rc = st.in(y3, vb, &d))) return rc; job.y3 = (const double*)d;
+    if ((rc = stage_Omega_nu(p, st, Omega_nu, &job.Omega_nu))) return rc;
+    if ((rc = st.outp(f_out, vb, &o))) return rc; job.f_out = (double*)o;
+    if ((rc = st.outp(err_io, sizeof(int) * (size_t)n, &o, true))) return rc; job.err = (int*)o;
+    if ((rc = launch_job(p, null_tables(), job, stats, st))) return rc;
+    return st.finish();
+}
+
+extern "C" int rg_liouville(rg_plan* p, int32_t n, const double* y0, const double* y1, const double* y2, const double* f,
+                            const double* Omega_nu, double* out) {
+    if (!p || n < 0 || !f || !y0 || !y1 || !y2 || !Omega_nu || !out) return fail(-1, "bad argument");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    Job job; memset(&job, 0, sizeof(job));
+    job.mode = 4; job.n = n; job.sched = 1;
+    const size_t vb = sizeof(double) * (size_t)n * p->g.vecjl;
+    int rc; const void* d; void* o;
+    if ((rc = st.in(f, vb, &d))) return rc; job.f_in = (const double*)d;
+    if ((rc = st.in(y0, sizeof(double) * (size_t)n, &d))) return rc; job.y0 = (const double*)d;
+    if ((rc = st.in(y1, vb, &d))) return rc; job.y1 = (const double*)d;
+    if ((rc = st.in(y2, vb, &d))) return rc; job.y2 = (const double*)d;
+    if ((rc = stage_Omega_nu(p, st, Omega_nu, &job.Omega_nu))) return rc;
+    if ((rc = st.outp(out, vb, &o))) return rc; job.f_out = (double*)o;
+    if ((rc = launch_job(p, null_tables(), job, nullptr, st))) return rc;
+    return st.finish();
+}
+
+extern "C" int rg_generate_y(rg_plan* p, int32_t n, const double* f, const double* Omega_nu, double* y0, double* y1,
+                             double* y2, double* y3) {
+    if (!p || n < 0 || !f || !Omega_nu || !y0 || !y1 || !y2 || !y3) return fail(-1, "bad argument");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    Job job; memset(&job, 0, sizeof(job));
+    job.mode = 5; job.n = n; job.sched = 0;
+    const size_t vb = sizeof(double) * (size_t)n * p->g.vecjl;
+    int rc; const void* d; void* o;
+    if ((rc = st.in(f, vb, &d))) return rc; job.f_in = (const double*)d;
+    if ((rc = stage_Omega_nu(p, st, Omega_nu, &job.Omega_nu))) return rc;
+    if ((rc = st.outp(y0, sizeof(double) * (size_t)n, &o))) return rc; job.y0_out = (double*)o;
+    if ((rc = st.outp(y1, vb, &o))) return rc; job.y1_out = (double*)o;
+    if ((rc = st.outp(y2, vb, &o))) return rc; job.y2_out = (double*)o;
+    if ((rc = st.outp(y3, vb, &o))) return rc; job.y3_out = (double*)o;
+    if ((rc = launch_job(p, null_tables(), job, nullptr, st))) return rc;
+    return st.finish();
+}
+
+extern "C" int rg_norm(rg_plan* p, int32_t n, const double* f, int32_t which, double* out) {
+    if (!p || n < 0 || !f || !out || which < 0 || which > 2) return fail(-1, "bad argument");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    int rc; const void* d; void* o;
+    if ((rc = st.in(f, sizeof(double) * (size_t)n * p->g.vecjl, &d))) return rc;
+    if ((rc = st.outp(out, sizeof(double) * (size_t)n, &o))) return rc;
+    if (n > 0) {
+        norm_kernel<<<std::min(n, 148 * 8), 256, 0, p->stream>>>(p->dp, n, (const double*)d, which, (double*)o);
+        CU(cudaGetLastError());
+    }
+    return st.finish();
+}
+
+extern "C" int rg_sym(rg_plan* p, int32_t n, const double* f, double* out) {
+    if (!p || n < 0 || !f || !out) return fail(-1, "bad argument");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    int rc; const void* d; void* o;
+    const size_t vb = sizeof(double) * (size_t)n * p->g.vecjl;
+    if ((rc = st.in(f, vb, &d))) return rc;
+    if ((rc = st.outp(out, vb, &o))) return rc;
+    if (n > 0) {
+        sym_kernel<<<std::min(n, 148 * 8), 256, 0, p->stream>>>(p->dp, n, (const double*)d, (double*)o);
+        CU(cudaGetLastError());
+    }
+    return st.finish();
+}
+
+extern "C" int rg_reindex_rescale(rg_plan* p, const rg_tables* tab, int32_t n, const double* f, const int32_t* k0, double* out) {
+    if (!p || !tab || n < 0 || !f || !out) return fail(-1, "bad argument");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    int rc; const void* d; const void* dk; void* o;
+    const size_t vb = sizeof(double) * (size_t)n * p->g.vecjl;
+    if ((rc = st.in(f, vb, &d))) return rc;
+    if ((rc = st.in(k0, sizeof(int) * (size_t)n, &dk))) return rc;
+    if ((rc = st.outp(out, vb, &o))) return rc;
+    if (n > 0) {
+        reindex_kernel<<<std::min(n, 148 * 8), 256, 0, p->stream>>>(p->dp, tab->t, n, (const double*)d, (const int*)dk, (double*)o);
+        CU(cudaGetLastError());
+    }
+    return st.finish();
+}
+
+extern "C" int rg_conv_product(rg_plan* p, int32_t n, const double* f1, const double* f2, double* out) {
+    if (!p || n < 0 || !f1 || !f2 || !out) return fail(-1, "bad argument");
+    CU(cudaSetDevice(p->device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, p->device));
+    if ((size_t)2 * p->g.vecjl * 8 > (size_t)prop.sharedMemPerBlockOptin) return fail(-5, "operands do not fit in shared memory");
+    Stage st(p);
+    int rc; const void* d1; const void* d2; void* o;
+    const size_t vb = sizeof(double) * (size_t)n * p->g.vecjl;
+    if ((rc = st.in(f1, vb, &d1))) return rc;
+    if ((rc = st.in(f2, vb, &d2))) return rc;
+    if ((rc = st.outp(out, vb, &o))) return rc;
+    if (n > 0) {
+        conv_kernel<<<std::min(n, 148 * 2), 256, 2 * p->g.vecjl * 8, p->stream>>>(p->dp, n, (const double*)d1, (const double*)d2, (double*)o);
+        CU(cudaGetLastError());
+    }
+    return st.finish();
+}
+
+extern "C" int rg_compute_m_s(rg_plan* p, int32_t n, const double* y0, const double* y1, const double* y2,
+                              const double* Omega_nu, int32_t* m_star, int32_t* scale, double* norm1) {
+    (void)p; (void)n; (void)y0; (void)y1; (void)y2; (void)Omega_nu; (void)m_star; (void)scale; (void)norm1;
+    return fail(-7, "rg_compute_m_s not available in this build");
+}
+
+// ---- host-only schedule introspection (tests replay it in numpy; no device needed)
+extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_t* iminus_wrapped, int32_t dense,
+                                 int32_t* n_warps, int32_t** lane_out, int32_t** pieces, int32_t* n_entries,
+                                 uint32_t** entries, int32_t* n_support, int32_t** supp_rec) {
+    if (dim < 1 || dim > 3 || J < 1 || J > 15 || L < 1) return fail(-2, "bad geometry");
+    rgplan::Geometry g; g.init(dim, L, J);
+    std::vector<uint16_t> mask = masks_from_iminus(g, iminus_wrapped);
+    rgplan::Schedule s = rgplan::make_schedule(g, mask, dense != 0);
+    *n_warps = s.n_warps; *n_entries = (int)s.entries.size() / 2; *n_support = s.n_support;
+    *lane_out = (int32_t*)malloc(sizeof(int32_t) * s.lane_out.size());
+    memcpy(*lane_out, s.lane_out.data(), sizeof(int32_t) * s.lane_out.size());
+    *pieces = (int32_t*)malloc(sizeof(int32_t) * 4 * s.pieces.size());
+    memcpy(*pieces, s.pieces.data(), sizeof(int32_t) * 4 * s.pieces.size());
+    *entries = (uint32_t*)malloc(sizeof(uint32_t) * std::max<size_t>(s.entries.size(), 1));
+    memcpy(*entries, s.entries.data(), sizeof(uint32_t) * s.entries.size());
+    *supp_rec = (int32_t*)malloc(sizeof(int32_t) * s.supp_rec.size());
+    memcpy(*supp_rec, s.supp_rec.data(), sizeof(int32_t) * s.supp_rec.size());
+    return 0;
+}
+extern "C" void rg_debug_free(void* p) { free(p); }

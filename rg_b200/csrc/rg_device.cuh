@@ -1,0 +1,502 @@
+// rg_device.cuh -- device side of the B200-native RG hot path (sm_100a).
+//
+// One CTA owns one Hamiltonian for a whole `converge` (RG.py:278-290): the Lie-series operands live in
+// shared memory as per-mode records, the coefficient array f and the generator y live in an
+// L2-resident per-CTA workspace, every loop of the reference (series, Lie steps, rg_map iterates)
+// runs on the device.  Compile with -fmad=false: only the explicit fma() of the convolution loops
+// fuse, the elementwise arithmetic rounds like the reference's numpy expressions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rgdev {
+
+struct Sched {
+    int n_warps, n_support;
+    const int* lane_out;         // [NW*32] centred mode of each lane, -1 idle
+    const uint32_t* lane_coord;  // [NW*32] packed biased coords
+    const int4* pieces;          // [NW*2] {box_warp, begin, end, mode}
+    const uint2* entries;        // {packed coords of nu1, (rec<<8)|jm}
+    const int* supp_rec;         // [M] record of centred mode or -1
+};
+
+struct DevPlan {
+    int dim, L, J, JP, n1, M, vecjl, off2, rec_units, idx_y1J;
+    int stride0, stride1, stride2;
+    int norm_choice;
+    double norm_analytic;
+    double tol_min, tol_max;
+    int max_lie, ct;
+    double min_step, abs_tol, rel_tol, eigenvalue;
+    int max_series;
+    const double* omega0_nu;  // [M] centred
+    const uint16_t* mask;     // [M] I^- bits per Taylor level
+    const int* reidx;         // [M] centred -> centred source, -1 masked
+    const double* normw;      // [M] exp(NormAnalytic*|nu|_1)
+    const int* c2w;           // [M] centred -> wrapped index
+    const double* theta;
+    int n_theta;
+    Sched sched[2];           // 0: I^- support (fused path), 1: dense (caller-supplied y)
+};
+
+// workspace arrays of one CTA (each vecjl doubles, layout [j][centred nu])
+enum { WS_FA = 0, WS_FB, WS_Y1, WS_Y2, WS_Y3, WS_H1, WS_H2, WS_T0, WS_T1, WS_T2, WS_T3, WS_T4, WS_T5, WS_T6, WS_T7, WS_COUNT };
+
+// Plans live in constant memory (uniform-datapath loads inside the device functions); a launch names
+// its plan by slot.  Shared-memory pointers are always re-derived from the __shared__ symbol so that
+// the compiler emits LDS/STS, never generic loads.
+#define RG_MAX_PLANS 16
+__constant__ DevPlan c_plan[RG_MAX_PLANS];
+extern __shared__ double2 smem_dyn[];
+
+struct Ctx {
+    int slot;     // index into c_plan
+    int sidx;     // schedule index (0 sparse, 1 dense)
+    double* ws;   // this CTA's global workspace
+    const double* Omega_nu;  // current Omega.nu, centred, global
+    long long n_liou, n_lie;
+};
+
+struct Smem {
+    double2* G;   // (M+1) records, the last one all zero
+    double2* Y;   // n_support records
+    double* out;  // [M][JP]
+    double* red;  // 64 doubles of reduction scratch (+ 16 bytes for the work ticket)
+};
+__device__ __forceinline__ Smem smem_view(const DevPlan& P, const Sched& S) {
+    Smem v;
+    v.G = smem_dyn;
+    v.Y = v.G + (P.M + 1) * P.rec_units;
+    v.out = reinterpret_cast<double*>(v.Y + S.n_support * P.rec_units);
+    v.red = v.out + P.M * P.JP;
+    return v;
+}
+#define RG_PLAN(c) c_plan[(c).slot]
+#define RG_SCHED(c) c_plan[(c).slot].sched[(c).sidx]
+
+__device__ __forceinline__ double pmax(double a, double b) { return (a > b || a != a) ? a : b; }
+
+__device__ __forceinline__ void norm_acc(int type, double& p, double x, double w) {
+    double ax = fabs(x);
+    if (type == 0) p += ax;
+    else if (type == 1) p = pmax(p, ax);
+    else if (type == 2) p += ax * ax;
+    else p = pmax(p, ax * w);
+}
+__device__ __forceinline__ double norm_fin(int type, double p) { return type == 2 ? sqrt(p) : p; }
+
+// deterministic two-value block reduction (fixed shuffle tree, fixed cross-warp order)
+__device__ __forceinline__ double2 block_reduce2(double* red, int type, double a, double b) {
+    const bool ismax = (type == 1 || type == 3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        double a2 = __shfl_down_sync(0xffffffffu, a, o), b2 = __shfl_down_sync(0xffffffffu, b, o);
+        if (ismax) { a = pmax(a, a2); b = pmax(b, b2); } else { a += a2; b += b2; }
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) { red[w] = a; red[32 + w] = b; }
+    __syncthreads();
+    double ra = red[0], rb = red[32];
+    for (int i = 1; i < nw; ++i) {
+        if (ismax) { ra = pmax(ra, red[i]); rb = pmax(rb, red[32 + i]); } else { ra += red[i]; rb += red[32 + i]; }
+    }
+    __syncthreads();
+    return make_double2(norm_fin(type, ra), norm_fin(type, rb));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Taylor product of one (nu1, nu2) pair: acc[j] += sum_{j1+j2=j} dAy[j1]*Omg[j2] - Omy[j1]*dAg[j2]
+// record layout (doubles): [0..J-1] d-type, [OFF2..OFF2+J] Omega-type, y1[J] (caller-supplied y only) at IDXJ
+template <int J>
+__device__ __forceinline__ void taylor(double (&acc)[J + 1], const double2* __restrict__ gp,
+                                       const double2* __restrict__ yp, int jm) {
+    constexpr int JP = J + 1, OFF2 = J + (J & 1), TOT = OFF2 + JP, NU2 = (TOT + 1) / 2;
+    constexpr int IDXJ = (J & 1) ? J : OFF2 + JP;
+    double g[2 * NU2];
+#pragma unroll
+    for (int u = 0; u < NU2; ++u) { double2 t = gp[u]; g[2 * u] = t.x; g[2 * u + 1] = t.y; }
+    // conv(dA y, Omega g): y1[j1] = yd[j1], needs j1+1 < jm ; B1[j2] = g[OFF2+j2]
+#pragma unroll
+    for (int u = 0; 2 * u < J; ++u) {
+        if (2 * u + 1 < jm) {
+            double2 t = yp[u];
+            {
+                const int j1 = 2 * u;
+#pragma unroll
+                for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, g[OFF2 + j2], acc[j1 + j2]);
+            }
+            if (2 * u + 1 < J && 2 * u + 2 < jm) {
+                const int j1 = 2 * u + 1;
+#pragma unroll
+                for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.y, g[OFF2 + j2], acc[j1 + j2]);
+            }
+        }
+    }
+    if (JP < jm) {  // caller-supplied y with y1[J] != 0 (never on the fused path)
+        double a = reinterpret_cast<const double*>(yp)[IDXJ];
+        acc[J] = fma(a, g[OFF2], acc[J]);
+    }
+    // conv(Omega y, dA g): y2[j1] = yd[OFF2+j1], needs j1 < jm ; B2[j2] = g[j2], j2 < J
+#pragma unroll
+    for (int u = 0; 2 * u <= J; ++u) {
+        if (2 * u < jm) {
+            double2 t = yp[OFF2 / 2 + u];
+            {
+                const int j1 = 2 * u;
+#pragma unroll
+                for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, g[j2], acc[j1 + j2]);
+            }
+            if (2 * u + 1 <= J && 2 * u + 1 < jm) {
+                const int j1 = 2 * u + 1;
+#pragma unroll
+                for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.y, g[j2], acc[j1 + j2]);
+            }
+        }
+    }
+}
+
+template <int J>
+__device__ __forceinline__ void conv_piece(const Ctx& c, int box_warp, int e_begin, int e_end, double (&acc)[J + 1]) {
+    const DevPlan& P = RG_PLAN(c);
+    const Sched& S = RG_SCHED(c);
+    const Smem sm = smem_view(P, S);
+    const double2* const G = sm.G;
+    const double2* const Y = sm.Y;
+    const uint2* const entries = S.entries;
+    const int lane = threadIdx.x & 31;
+    const uint32_t mc = S.lane_coord[box_warp * 32 + lane];
+    const int L = P.L, s0 = P.stride0, s1 = P.stride1, s2 = P.stride2, Mz = P.M;
+    const int v0 = (int)(mc & 0xff) + L, v1 = (int)((mc >> 8) & 0xff) + L, v2 = (int)((mc >> 16) & 0xff) + L;
+    const unsigned lim = 2u * (unsigned)L;
+    const int RU = P.rec_units;
+#pragma unroll
+    for (int j = 0; j <= J; ++j) acc[j] = 0.0;
+    for (int base = e_begin; base < e_end; base += 32) {
+        uint2 me = make_uint2(0u, 0u);
+        if (base + lane < e_end) me = entries[base + lane];
+        const int cnt = min(32, e_end - base);
+        for (int i = 0; i < cnt; ++i) {
+            const uint32_t ec = __shfl_sync(0xffffffffu, me.x, i);
+            const uint32_t ei = __shfl_sync(0xffffffffu, me.y, i);
+            const int jm = (int)(ei & 0xff);
+            const int rec = (int)(ei >> 8);
+            const int u0 = v0 - (int)(ec & 0xff), u1 = v1 - (int)((ec >> 8) & 0xff), u2 = v2 - (int)((ec >> 16) & 0xff);
+            const bool ok = ((unsigned)u0 <= lim) & ((unsigned)u1 <= lim) & ((unsigned)u2 <= lim);
+            const int gi = ok ? (u0 * s0 + u1 * s1 + u2 * s2) : Mz;
+            taylor<J>(acc, G + gi * RU, Y + rec * RU, jm);
+        }
+    }
+}
+
+// out[nu][j] = conv(dA y, Omega g) - conv(Omega y, dA g)  (G, Y in shared memory).  Ends with a barrier.
+template <int J>
+__device__ __noinline__ void conv_all(Ctx& c) {
+    constexpr int JP = J + 1;
+    const Sched& S = RG_SCHED(c);
+    double* const out = smem_view(RG_PLAN(c), S).out;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc[JP];
+    const int4 p0 = S.pieces[w * 2 + 0];
+    const int4 p1 = S.pieces[w * 2 + 1];
+    if (p0.w == 1) {
+        conv_piece<J>(c, p0.x, p0.y, p0.z, acc);
+        const int nu = S.lane_out[p0.x * 32 + lane];
+        if (nu >= 0) {
+#pragma unroll
+            for (int j = 0; j < JP; ++j) out[nu * JP + j] = acc[j];
+        }
+    }
+    if (p1.w == 2) conv_piece<J>(c, p1.x, p1.y, p1.z, acc);
+    __syncthreads();
+    if (p1.w == 2) {
+        const int nu = S.lane_out[p1.x * 32 + lane];
+        if (nu >= 0) {
+#pragma unroll
+            for (int j = 0; j < JP; ++j) out[nu * JP + j] += acc[j];
+        }
+    }
+    __syncthreads();
+    c.n_liou++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// records of g: d-type = dA g (RG.py:76 roll(f*J_,-1)), Omega-type = Omega_nu*g.  src: global [j][nu].
+__device__ __noinline__ void build_G(const Ctx& c, const double* __restrict__ src) {
+    const DevPlan& P = RG_PLAN(c);
+    const int M = P.M, J = P.J;
+    const Smem sm = smem_view(P, RG_SCHED(c));
+    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+        double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
+        const double om = c.Omega_nu[nu];
+        double prev = src[nu];
+        for (int j = 0; j <= J; ++j) {
+            r[P.off2 + j] = om * prev;
+            if (j < J) { double nx = src[(j + 1) * M + nu]; r[j] = nx * (double)(j + 1); prev = nx; }
+        }
+    }
+}
+
+// records of y scaled by `step` (item*step, RG.py:176) or divided by `scale` (item/scale, RG.py:156)
+__device__ __noinline__ void build_Y(const Ctx& c, double step, double divisor, bool use_div) {
+    const DevPlan& P = RG_PLAN(c);
+    const int M = P.M, J = P.J;
+    const double* y1 = c.ws + (size_t)WS_Y1 * P.vecjl;
+    const double* y2 = c.ws + (size_t)WS_Y2 * P.vecjl;
+    const Sched& S = RG_SCHED(c);
+    const Smem sm = smem_view(P, S);
+    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+        const int rec = S.supp_rec[nu];
+        if (rec < 0) continue;
+        double* r = reinterpret_cast<double*>(sm.Y + rec * P.rec_units);
+        for (int j = 0; j <= J; ++j) {
+            double a = y1[j * M + nu], b = y2[j * M + nu];
+            a = use_div ? a / divisor : a * step;
+            b = use_div ? b / divisor : b * step;
+            r[j < J ? j : P.idx_y1J] = a;
+            r[P.off2 + j] = b;
+        }
+    }
+}
+
+// One series term: sh = [y3 +] (a0*dA g + conv) [/ m]; f += sh; G <- records of sh.
+// Returns (norm(sh), norm(f)).  Thread <-> mode nu.
+template <int J>
+__device__ __noinline__ double2 series_epilogue(Ctx& c, double* __restrict__ f, double a0, bool first, double y3mul,
+                                                   double y3div, bool use_div, double m) {
+    constexpr int JP = J + 1;
+    const DevPlan& P = RG_PLAN(c);
+    const int M = P.M, type = P.norm_choice;
+    const double* y3 = c.ws + (size_t)WS_Y3 * P.vecjl;
+    const Smem sm = smem_view(P, RG_SCHED(c));
+    double ps = 0.0, pf = 0.0;
+    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+        double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
+        const double om = c.Omega_nu[nu];
+        const double w = (type == 3) ? P.normw[nu] : 1.0;
+        double sh[JP];
+#pragma unroll
+        for (int j = 0; j < JP; ++j) {
+            const double dg = (j < J) ? r[j] : 0.0;
+            double v = a0 * dg + sm.out[nu * JP + j];
+            if (first) {
+                double t = y3[j * M + nu];
+                t = use_div ? t / y3div : t * y3mul;
+                v = t + v;
+            } else {
+                v = v / m;
+            }
+            sh[j] = v;
+            const double fn = f[j * M + nu] + v;
+            f[j * M + nu] = fn;
+            norm_acc(type, ps, v, w);
+            norm_acc(type, pf, fn, w);
+        }
+#pragma unroll
+        for (int j = 0; j < JP; ++j) {
+            r[P.off2 + j] = om * sh[j];
+            if (j < J) r[j] = sh[j + 1] * (double)(j + 1);
+        }
+    }
+    return block_reduce2(sm.red, type, ps, pf);
+}
+
+__device__ __noinline__ void copy_arr(const Ctx& c, double* dst, const double* src) {
+    const int n = RG_PLAN(c).vecjl;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// RG.expm_onestep (RG.py:173-192) in place on f (global).  y in WS_Y1..3, a_unscaled = y[0].
+template <int J>
+__device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, double step, double divisor, bool use_div, int m_star) {
+    const DevPlan& P = RG_PLAN(c);
+    const double tol = 1.1102230246251565e-16;
+    const double a0 = use_div ? a_unscaled / divisor : a_unscaled * step;
+    int err = 0;
+    build_Y(c, step, divisor, use_div);
+    build_G(c, f);
+    __syncthreads();
+    conv_all<J>(c);
+    double2 r = series_epilogue<J>(c, f, a0, true, step, divisor, use_div, 1.0);
+    double c1 = r.x;
+    for (int m = 2; m_star <= 0 || m <= m_star; ++m) {
+        conv_all<J>(c);
+        r = series_epilogue<J>(c, f, a0, false, 0.0, 1.0, false, (double)m);
+        const double c2 = r.x;
+        if (c1 + c2 < tol * r.y) break;
+        else if (c1 + c2 > P.tol_max) { err = 1; break; }
+        c1 = c2;
+        if (m >= P.max_series) { err = 1; break; }  // safety: the reference would spin (quirk Q6)
+    }
+    return err;
+}
+
+template <int J>
+__device__ __forceinline__ int expm_onestep(Ctx& c, double* f, double a_unscaled, double step) {
+    return expm_series<J>(c, f, a_unscaled, step, 1.0, false, 0);
+}
+
+// norm(h1 - h2), norm(h1)
+__device__ __noinline__ double2 diff_norms(const Ctx& c, const double* h1, const double* h2) {
+    const DevPlan& P = RG_PLAN(c);
+    const int M = P.M, type = P.norm_choice;
+    double pd = 0.0, p1 = 0.0;
+    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+        const double w = (type == 3) ? P.normw[nu] : 1.0;
+        for (int j = 0; j <= P.J; ++j) {
+            const double a = h1[j * M + nu], b = h2[j * M + nu];
+            norm_acc(type, pd, a - b, w);
+            norm_acc(type, p1, a, w);
+        }
+    }
+    return block_reduce2(smem_view(P, RG_SCHED(c)).red, type, pd, p1);
+}
+
+// RG.expm_adapt (RG.py:194-205): the recursion unrolled into a depth-first stack of sub-steps.
+template <int J>
+__device__ __noinline__ int expm_adapt(Ctx& c, double* f, double a_unscaled, double step0, int err_in) {
+    const DevPlan& P = RG_PLAN(c);
+    double* h1 = c.ws + (size_t)WS_H1 * P.vecjl;
+    double* h2 = c.ws + (size_t)WS_H2 * P.vecjl;
+    double stack[64];
+    int sp = 0, err = err_in;
+    stack[sp++] = step0;
+    while (sp > 0) {
+        const double s = stack[--sp];
+        if (s < P.min_step || sp >= 60) {  // RG.py:196-198 (error=4 is dead, quirk Q3)
+            err = expm_onestep<J>(c, f, a_unscaled, s);
+            __syncthreads();
+            continue;
+        }
+        copy_arr(c, h1, f);
+        copy_arr(c, h2, f);
+        __syncthreads();
+        expm_onestep<J>(c, h1, a_unscaled, s);
+        __syncthreads();
+        expm_onestep<J>(c, h2, a_unscaled, 0.5 * s);
+        __syncthreads();
+        expm_onestep<J>(c, h2, a_unscaled, 0.5 * s);
+        __syncthreads();
+        const double2 r = diff_norms(c, h1, h2);
+        if (r.x < P.abs_tol + P.rel_tol * r.y) {
+            for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) f[i] = 0.75 * h1[i] + 0.25 * h2[i];
+            __syncthreads();
+        } else {
+            stack[sp++] = 0.5 * s;
+            stack[sp++] = 0.5 * s;
+        }
+    }
+    return err;
+}
+
+// RG.generate_y (RG.py:108-113): writes unscaled y1,y2,y3 to WS_Y1..3; returns y[0]
+__device__ __noinline__ double generate_y(const Ctx& c, const double* __restrict__ f) {
+    const DevPlan& P = RG_PLAN(c);
+    const int M = P.M, J = P.J, c0 = (M - 1) / 2;
+    double* y1 = c.ws + (size_t)WS_Y1 * P.vecjl;
+    double* y2 = c.ws + (size_t)WS_Y2 * P.vecjl;
+    double* y3 = c.ws + (size_t)WS_Y3 * P.vecjl;
+    const double f2 = f[2 * M + c0], f1 = f[1 * M + c0];
+    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+        const unsigned mk = P.mask[nu];
+        const double om0 = P.omega0_nu[nu], om = c.Omega_nu[nu];
+        double yprev = 0.0;
+        for (int j = 0; j <= J; ++j) {
+            double y = 0.0;
+            if ((mk >> j) & 1u) {
+                if (j == 0) y = f[nu] / om0;
+                else y = (f[j * M + nu] - 2 * f2 * om * yprev) / om0;
+            }
+            if (j >= 1) y1[(j - 1) * M + nu] = y * (double)j;
+            y2[j * M + nu] = om * y;
+            y3[j * M + nu] = -om0 * y;
+            yprev = y;
+        }
+        y1[J * M + nu] = 0.0;
+    }
+    return -f1 / (2 * f2);
+}
+
+// RG.sym (RG.py:249-253) in place, fused with the I^- norm (RG.py:217-218,221) and norm_int (RG.py:244-247)
+__device__ __noinline__ double2 sym_and_norms(const Ctx& c, double* f, bool do_sym) {
+    const DevPlan& P = RG_PLAN(c);
+    const int M = P.M, type = P.norm_choice, c0 = (M - 1) / 2;
+    double pim = 0.0, pint = 0.0;
+    for (int nu = threadIdx.x; nu <= c0; nu += blockDim.x) {
+        const int mu = M - 1 - nu;
+        const unsigned mk_a = P.mask[nu], mk_b = P.mask[mu];
+        const double wa = (type == 3) ? P.normw[nu] : 1.0, wb = (type == 3) ? P.normw[mu] : 1.0;
+        for (int j = 0; j <= P.J; ++j) {
+            double a = f[j * M + nu], b = f[j * M + mu];
+            if (do_sym) {
+                const double s1 = (a + b) / 2, s2 = (b + a) / 2;
+                a = s1; b = s2;
+                if (nu == c0 && j == 0) { a = 0.0; b = 0.0; }
+                f[j * M + nu] = a;
+                if (mu != nu) f[j * M + mu] = b;
+            }
+            if ((mk_a >> j) & 1u) norm_acc(type, pim, a, wa);
+            if (nu != c0) {
+                if ((mk_b >> j) & 1u) norm_acc(type, pim, b, wb);
+                norm_acc(type, pint, a, wa);
+                norm_acc(type, pint, b, wb);
+            }
+        }
+    }
+    return block_reduce2(smem_view(P, RG_SCHED(c)).red, type, pim, pint);
+}
+
+// head of RG.rg_map (RG.py:210-216): dst = ren[j] * src[j][sign*N*nu] on the mask, else 0
+__device__ __noinline__ void reindex_rescale(const Ctx& c, const double* __restrict__ src, double* __restrict__ dst, double nrm) {
+    const DevPlan& P = RG_PLAN(c);
+    const int M = P.M, J = P.J, c0 = (M - 1) / 2;
+    const double f2 = src[2 * M + c0];
+    const double base = 2 * nrm / P.eigenvalue * f2;
+    double* red = smem_view(P, RG_SCHED(c)).red;
+    if (threadIdx.x <= J) red[threadIdx.x] = pow(base, (double)(2 - (int)threadIdx.x)) / (2 * f2);
+    __syncthreads();
+    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+        const int s = P.reidx[nu];
+        for (int j = 0; j <= J; ++j) dst[j * M + nu] = (s >= 0 ? src[j * M + s] : 0.0) * red[j];
+    }
+    __syncthreads();
+}
+
+struct Tables {
+    int n_tab;
+    const double* nrm;       // [n_tab]
+    const double* Omega_nu;  // [(n_tab+1)][M] centred
+};
+
+template <int J> __device__ int expm_multiply(Ctx& c, double* f, double a_unscaled);  // rg_multiply.cuh
+
+// RG.rg_map (RG.py:207-228).  f points to the current array (WS_FA or WS_FB); returns the new current.
+template <int J>
+__device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, int k, int& err_out, double& norm_int_out) {
+    const DevPlan& P = RG_PLAN(c);
+    double* fa = c.ws + (size_t)WS_FA * P.vecjl;
+    double* fb = c.ws + (size_t)WS_FB * P.vecjl;
+    double* dst = (f == fa) ? fb : fa;
+    c.Omega_nu = T.Omega_nu + (size_t)(k + 1) * P.M;
+    reindex_rescale(c, f, dst, T.nrm[k]);
+    f = dst;
+    int err = 0, kl = 0;
+    double2 nn = sym_and_norms(c, f, false);
+    while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie) {
+        const double a = generate_y(c, f);
+        __syncthreads();
+        if (P.ct == 0) err = expm_onestep<J>(c, f, a, 1.0);
+        else if (P.ct == 1) err = expm_adapt<J>(c, f, a, 1.0, err);
+        else err = expm_multiply<J>(c, f, a);
+        __syncthreads();
+        nn = sym_and_norms(c, f, true);
+        ++kl;
+        c.n_lie++;
+    }
+    if (nn.x > P.tol_max) err = 2;
+    else if (kl >= P.max_lie) err = -2;
+    err_out = err;
+    norm_int_out = nn.y;
+    return f;
+}
+
+}  // namespace rgdev

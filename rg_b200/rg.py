@@ -1,0 +1,497 @@
+"""Host-side mirror of the reference's `RG` class and `Hamiltonian` (RG.py:44-332).
+
+Same constructor (the RG_dict parameter dictionary), same attributes, same method names, argument
+meaning and error behaviour; every numerical method body is a call through the ctypes C ABI
+(include/rg_b200.h) into hand-written sm_100a kernels.  There is no CPU fallback.
+
+Table construction in __init__ follows RG.py:51-100 with the same numpy/scipy calls, so the masks,
+re-index tables and per-iterate frequency tables uploaded to the GPU are the reference's own.
+"""
+import copy
+import ctypes
+import os
+import warnings
+
+import numpy as xp
+import scipy.linalg as la
+
+from . import _lib
+
+N_TAB = 256  # rg_map iterates tabulated per starting Omega (the reference's converge is uncapped, quirk Q6)
+
+CT_IDS = {"expm_onestep": 0, "expm_adapt": 1, "expm_multiply": 2}
+NORM_IDS = {"sum": 0, "max": 1, "Euclidean": 2, "Analytic": 3}
+WHICH_NORM, WHICH_NORM_INT, WHICH_NORM_IMINUS = 0, 1, 2
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, xp.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):  # torch tensor (host pinned or CUDA): plumbing only
+        return a.data_ptr()
+    return a
+
+
+def _f64(a):
+    return xp.ascontiguousarray(a, dtype=xp.float64)
+
+
+def load_theta():
+    """theta_m table of RG.py:98-100: theta_taylor.mat from the CWD if present (as the reference does),
+    else the packaged copy of the same numbers."""
+    if os.path.exists('theta_taylor.mat'):
+        import scipy.io
+        return xp.asarray(scipy.io.loadmat('theta_taylor.mat')['theta'][0], dtype=xp.float64)
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "theta_taylor.txt")
+    return xp.array([float(l) for l in open(path) if l.strip() and not l.startswith("#")])
+
+
+class Hamiltonian:
+    """RG.py:309-332"""
+
+    def __repr__(self):
+        return '{}({}, {}, {}, {})'.format(self.__class__.__name__, self.Omega, self.f, self.error, self.count)
+
+    def __str__(self):
+        return 'A {} in action-angle variables'.format(self.__class__.__name__)
+
+    def __init__(self, Omega, f, error=0, count=0):
+        self.Omega = Omega
+        self.f = f
+        self.error = error
+        self.count = count
+
+    def __add__(self, other):
+        return Hamiltonian(self.Omega, self.f + other.f, error=self.error, count=self.count)
+
+    def __sub__(self, other):
+        return Hamiltonian(self.Omega, self.f - other.f, error=self.error, count=self.count)
+
+    def __mul__(self, other):
+        if isinstance(other, float) or isinstance(other, int):
+            return Hamiltonian(self.Omega, other * self.f, error=self.error, count=self.count)
+        else:
+            raise TypeError('multiplication only defined with a float or a int')
+
+
+class RG:
+    def __repr__(self):
+        return '{self.__class__.__name__}({self.DictParams})'.format(self=self)
+
+    def __str__(self):
+        return '{}D renormalization with N = {}'.format(self.dim, self.N.tolist())
+
+    def __init__(self, parameters, device=None):
+        # RG.py:52-54
+        for key in parameters:
+            setattr(self, key, parameters[key])
+        self.DictParams = parameters
+        if xp.dtype(self.Precision) not in (xp.dtype(xp.float64), xp.dtype(xp.float32)):
+            raise ValueError("Precision=128 is not supported by the B200 backend (fp64 kernels only); use 32 or 64")
+        self.N = xp.asarray(self.N, dtype=int)
+        # RG.py:55-67
+        self.dim = len(self.omega0)
+        self.zero_ = self.dim * (0,)
+        self.one_ = self.dim * (1,)
+        self.L_ = self.dim * (self.L,)
+        self.nL_ = self.dim * (-self.L,)
+        self.axis_dim = tuple(range(1, self.dim + 1))
+        self.r_jl = (self.J + 1,) + self.dim * (2 * self.L + 1,)
+        self.r_1l = (1,) + self.dim * (2 * self.L + 1,)
+        self.r_j1 = (self.J + 1,) + self.dim * (1,)
+        self.vecjl = xp.prod(xp.asarray(self.r_jl))
+        self.conv_dim = xp.index_exp[:self.J + 1] + self.dim * xp.index_exp[self.L:3 * self.L + 1]
+        indx = self.dim * (xp.hstack((xp.arange(0, self.L + 1), xp.arange(-self.L, 0))),)
+        self.nu = xp.meshgrid(*indx, indexing='ij')
+        # RG.py:68-76
+        eigenval, w_eig = la.eig(self.N.T)
+        self.Eigenvalue = xp.real(eigenval[xp.abs(eigenval) < 1])[0]
+        N_nu = xp.sign(self.Eigenvalue).astype(int) * xp.einsum('ij,j...->i...', self.N, self.nu)
+        self.omega0_nu = xp.einsum('i,i...->...', self.omega0, self.nu).reshape(self.r_1l)
+        self.Omega_nu = xp.einsum('i,i...->...', self.Omega, self.nu).reshape(self.r_1l)
+        mask = xp.prod(abs(N_nu) <= self.L, axis=0, dtype=bool)
+        norm_nu = self.Precision(la.norm(self.nu, axis=0)).reshape(self.r_1l)
+        self.J_ = xp.arange(self.J + 1, dtype=self.Precision).reshape(self.r_j1)
+        self.derivs = lambda f: [xp.roll(f * self.J_, -1, axis=0), self.Omega_nu * f]
+        # RG.py:77-86
+        if self.ChoiceIm == 'AKW1998':
+            comp_im = self.Sigma * xp.repeat(norm_nu, self.J + 1, axis=0) + self.Kappa * self.J_
+        elif self.ChoiceIm == 'K1999':
+            comp_im = xp.maximum(self.Sigma * xp.repeat(norm_nu, self.J + 1, axis=0), self.Kappa * self.J_)
+        else:
+            w_nu = xp.einsum('ij,j...->i...', w_eig, self.nu)
+            norm_w_nu = la.norm(w_nu, axis=0).reshape(self.r_1l)
+            comp_im = self.Sigma * xp.repeat(norm_w_nu, self.J + 1, axis=0) + self.Kappa * self.J_
+        omega0_nu_ = xp.repeat(xp.abs(self.omega0_nu), self.J + 1, axis=0) / la.norm(self.omega0)
+        self.Iminus = omega0_nu_ > comp_im
+        # RG.py:87-91
+        self.nu_mask = xp.index_exp[:self.J + 1]
+        self.N_nu_mask = xp.index_exp[:self.J + 1]
+        for _ in range(self.dim):
+            self.nu_mask += (self.nu[_][mask],)
+            self.N_nu_mask += (N_nu[_][mask],)
+        # the same re-indexing as a gather table for the device: f'[nu] = f[N_nu] where mask, else 0
+        n1 = 2 * self.L + 1
+        flat = xp.zeros(self.r_1l[1:], dtype=xp.int64)
+        for d in range(self.dim):
+            flat = flat * n1 + (N_nu[d] % n1)
+        self._reidx = xp.where(mask, flat, -1).astype(xp.int32).reshape(-1)
+        self._M = int(n1 ** self.dim)
+        # RG.py:92-100: `norm` is a callable attribute, `theta` a dict m -> theta_m
+        self.norm = self._norm
+        array = load_theta()
+        self._theta = _f64(array)
+        self.theta = dict(zip(xp.arange(1, len(array) + 1), array.T))
+        self._device = device
+        self._plans = {}
+        self._tabs = {}
+        self.last_stats = None
+
+    def __getstate__(self):
+        # device handles do not pickle (the reference's drivers pickle `case` into Pool workers)
+        d = dict(self.__dict__)
+        d['_plans'] = {}
+        d['_tabs'] = {}
+        d.pop('norm', None)
+        d.pop('derivs', None)
+        return d
+
+    def __setstate__(self, d):
+        self.__dict__.update(d)
+        self.norm = self._norm
+        self.derivs = lambda f: [xp.roll(f * self.J_, -1, axis=0), self.Omega_nu * f]
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def close(self):
+        L = _lib._LIB
+        if L is None:
+            return
+        for t in self._tabs.values():
+            L.rg_tables_destroy(t[3])
+        self._tabs = {}
+        for p in self._plans.values():
+            L.rg_plan_destroy(p)
+        self._plans = {}
+
+    # ------------------------------------------------------------------ device plumbing
+    def _ct_name(self, ct=None):
+        return (self.CanonicalTransformation if ct is None else ct).replace('self.', '')
+
+    def _device_index(self):
+        if self._device is not None:
+            return int(self._device)
+        return int(os.environ.get("LOCAL_RANK", "0")) if os.environ.get("RG_B200_DEVICE_FROM_RANK", "1") == "1" else 0
+
+    def _plan(self, ct=None):
+        """One rg_plan per canonical transformation (the CT is a plan parameter on the fused path)."""
+        name = self._ct_name(ct)
+        if name not in CT_IDS:
+            raise ValueError("unknown CanonicalTransformation %r" % name)
+        if name not in self._plans:
+            L = _lib.lib()
+            if _lib.device_count() < 1:
+                raise _lib.RGError("no CUDA device visible: rg_b200 has no CPU fallback")
+            prm = _lib.RGParams()
+            prm.dim, prm.L, prm.J = self.dim, int(self.L), int(self.J)
+            prm.norm_choice = NORM_IDS.get(self.NormChoice, 0)
+            prm.norm_analytic = float(self.NormAnalytic)
+            prm.tol_min, prm.tol_max, prm.max_lie = float(self.TolMin), float(self.TolMax), int(self.MaxLie)
+            prm.ct = CT_IDS[name]
+            prm.min_step, prm.abs_tol, prm.rel_tol = float(self.MinStep), float(self.AbsTol), float(self.RelTol)
+            prm.eigenvalue = float(self.Eigenvalue)
+            self._k_om0 = _f64(self.omega0_nu.reshape(-1))
+            self._k_im = xp.ascontiguousarray(self.Iminus.reshape(-1), dtype=xp.uint8)
+            prm.omega0_nu = self._k_om0.ctypes.data
+            prm.iminus = self._k_im.ctypes.data
+            prm.reidx = self._reidx.ctypes.data
+            prm.theta = self._theta.ctypes.data
+            prm.n_theta = len(self._theta)
+            prm.device = self._device_index()
+            prm.max_series = 0
+            h = ctypes.c_void_p()
+            _lib.check(L.rg_plan_create(ctypes.byref(prm), ctypes.byref(h)))
+            self._plans[name] = h
+        return self._plans[name]
+
+    def _tables(self, Omega):
+        """(nrm_tab, Omega_nu_tab, [Omega_k], device handle) from a starting Omega, computed with the
+        reference's own calls (RG.py:210-213): Omega_ = N.T.dot(Omega); la.norm; einsum."""
+        Om = xp.asarray(Omega)
+        key = _f64(Om).tobytes()
+        if key not in self._tabs:
+            nrm = xp.empty(N_TAB)
+            onu = xp.empty((N_TAB + 1, self._M))
+            oms = [Om]
+            onu[0] = xp.einsum('i,i...->...', Om, self.nu).reshape(-1)
+            for k in range(N_TAB):
+                Omega_ = self.N.T.dot(Om)
+                nrm[k] = la.norm(Omega_)
+                Om = Omega_ / la.norm(Omega_)
+                oms.append(Om)
+                onu[k + 1] = xp.einsum('i,i...->...', Om, self.nu).reshape(-1)
+            h = ctypes.c_void_p()
+            _lib.check(_lib.lib().rg_tables_create(self._plan(), N_TAB, nrm.ctypes.data, onu.ctypes.data, ctypes.byref(h)))
+            if len(self._tabs) > 64:
+                k0, t0 = next(iter(self._tabs.items()))
+                _lib.lib().rg_tables_destroy(t0[3])
+                del self._tabs[k0]
+            self._tabs[key] = (nrm, onu, oms, h)
+        return self._tabs[key]
+
+    def plan_info(self, ct=None):
+        t, s, c, n = (ctypes.c_int32() for _ in range(4))
+        fu, fe = ctypes.c_int64(), ctypes.c_int64()
+        _lib.check(_lib.lib().rg_plan_info(self._plan(ct), ctypes.byref(t), ctypes.byref(s), ctypes.byref(c),
+                                            ctypes.byref(n), ctypes.byref(fu), ctypes.byref(fe)))
+        return dict(threads_per_cta=t.value, smem_bytes=s.value, ctas_per_sm=c.value, n_support=n.value,
+                    fma_useful_per_liouville=fu.value, fma_executed_per_liouville=fe.value)
+
+    def _Omega_nu_flat(self):
+        return _f64(xp.asarray(self.Omega_nu).reshape(-1))
+
+    def _stats(self):
+        self.last_stats = _lib.RGStats()
+        return ctypes.byref(self.last_stats)
+
+    # ------------------------------------------------------------------ RG.py:92-97
+    def _norm(self, f):
+        f = _f64(f).reshape(1, -1)
+        if f.shape[1] != self.vecjl:
+            raise ValueError("norm expects an array of shape %s" % (self.r_jl,))
+        out = xp.empty(1)
+        _lib.check(_lib.lib().rg_norm(self._plan(), 1, f.ctypes.data, WHICH_NORM, out.ctypes.data))
+        return out[0]
+
+    def norm_batch(self, f, which=WHICH_NORM):
+        """Batched norm over f[B, ...] (host ndarray or device pointer holder); returns ndarray[B]."""
+        f = _f64(f).reshape(-1, int(self.vecjl))
+        out = xp.empty(f.shape[0])
+        _lib.check(_lib.lib().rg_norm(self._plan(), f.shape[0], f.ctypes.data, which, out.ctypes.data))
+        return out
+
+    # ------------------------------------------------------------------ RG.py:102-117
+    def conv_product(self, fun1, fun2):
+        a, b = _f64(fun1), _f64(fun2)
+        out = xp.empty(self.r_jl)
+        _lib.check(_lib.lib().rg_conv_product(self._plan(), 1, a.ctypes.data, b.ctypes.data, out.ctypes.data))
+        return out
+
+    def generate_y(self, h):
+        f = _f64(h.f)
+        onu = self._Omega_nu_flat()
+        y0 = xp.empty(1)
+        y1, y2, y3 = xp.empty(self.r_jl), xp.empty(self.r_jl), xp.empty(self.r_jl)
+        _lib.check(_lib.lib().rg_generate_y(self._plan(), 1, f.ctypes.data, onu.ctypes.data, y0.ctypes.data,
+                                            y1.ctypes.data, y2.ctypes.data, y3.ctypes.data))
+        return y0[0], y1, y2, y3
+
+    def liouville(self, y, f):
+        f = _f64(f).reshape(self.r_jl)
+        onu = self._Omega_nu_flat()
+        y0 = xp.array([y[0]], dtype=xp.float64)
+        y1, y2 = _f64(y[1]), _f64(y[2])
+        out = xp.empty(self.r_jl)
+        _lib.check(_lib.lib().rg_liouville(self._plan(), 1, y0.ctypes.data, y1.ctypes.data, y2.ctypes.data, f.ctypes.data,
+                                           onu.ctypes.data, out.ctypes.data))
+        return out
+
+    # ------------------------------------------------------------------ RG.py:119-150
+    def compute_p_max(self, m_max):
+        sqrt_m_max = xp.sqrt(m_max)
+        p_low, p_high = int(xp.floor(sqrt_m_max)), int(xp.ceil(sqrt_m_max + 1))
+        return max(p for p in range(p_low, p_high + 1) if p * (p - 1) <= m_max + 1)
+
+    def _m_s(self, y):
+        onu = self._Omega_nu_flat()
+        y0 = xp.array([y[0]], dtype=xp.float64)
+        y1, y2 = _f64(y[1]), _f64(y[2])
+        m, s = xp.zeros(1, xp.int32), xp.zeros(1, xp.int32)
+        n1 = xp.zeros(1)
+        _lib.check(_lib.lib().rg_compute_m_s(self._plan(), 1, y0.ctypes.data, y1.ctypes.data, y2.ctypes.data, onu.ctypes.data,
+                                             m.ctypes.data, s.ctypes.data, n1.ctypes.data))
+        return int(m[0]), int(s[0]), float(n1[0])
+
+    def pnorm(self, y, p=1):
+        if p != 1:
+            raise NotImplementedError("pnorm(p>1) is evaluated inside compute_m_s on the device")
+        return self._m_s(y)[2]
+
+    def compute_m_s(self, y, n0=1, tol=2**-53, ell=2):
+        m, s, _ = self._m_s(y)
+        return m, s
+
+    # ------------------------------------------------------------------ RG.py:152-205
+    def _expm(self, ct, h, y, step):
+        h_ = copy.deepcopy(h)
+        f = _f64(h.f)
+        onu = self._Omega_nu_flat()
+        y0 = xp.array([y[0]], dtype=xp.float64)
+        y1, y2, y3 = _f64(y[1]), _f64(y[2]), _f64(y[3])
+        out = xp.empty(self.r_jl)
+        err = xp.array([h.error], dtype=xp.int32)
+        _lib.check(_lib.lib().rg_expm(self._plan(), CT_IDS[ct], 1, f.ctypes.data, y0.ctypes.data, y1.ctypes.data,
+                                      y2.ctypes.data, y3.ctypes.data, onu.ctypes.data, float(step), out.ctypes.data,
+                                      err.ctypes.data, self._stats()))
+        h_.f = out
+        h_.error = int(err[0])
+        return h_
+
+    def expm_multiply(self, h, y, tol=2**-53):
+        return self._expm("expm_multiply", h, y, 1.0)
+
+    def expm_onestep(self, h, y, step=1, tol=2**-53):
+        return self._expm("expm_onestep", h, y, step)
+
+    def expm_adapt(self, h, y, step=1.0):
+        return self._expm("expm_adapt", h, y, step)
+
+    # ------------------------------------------------------------------ RG.py:207-228
+    def rg_map(self, h):
+        h_ = copy.deepcopy(h)
+        nrm, onu, oms, tab = self._tables(h.Omega)
+        f = _f64(h.f)
+        out = xp.empty(self.r_jl)
+        err = xp.zeros(1, xp.int32)
+        _lib.check(_lib.lib().rg_map(self._plan(), tab, 1, f.ctypes.data, None, 1, out.ctypes.data, err.ctypes.data,
+                                     self._stats()))
+        h_.f = out
+        h_.error = int(err[0])
+        h_.Omega = oms[1]
+        self.Omega_nu = onu[1].reshape(self.r_1l).copy()   # RG.py:213 mutates the RG object
+        if h_.error == -2:
+            warnings.warn('Maximum number of Lie transforms reached (MaxLie)')
+        return h_
+
+    def rg_map_batch(self, f, Omega, n_iter=1):
+        """n_iter rg_maps on a batch f[B, ...] sharing one starting Omega; returns (f_out, err[B])."""
+        nrm, onu, oms, tab = self._tables(Omega)
+        f = _f64(f).reshape(-1, int(self.vecjl))
+        out = xp.empty_like(f)
+        err = xp.zeros(f.shape[0], xp.int32)
+        _lib.check(_lib.lib().rg_map(self._plan(), tab, f.shape[0], f.ctypes.data, None, int(n_iter), out.ctypes.data,
+                                     err.ctypes.data, self._stats()))
+        return out.reshape((-1,) + self.r_jl), err
+
+    def eigenvalues(self, h, dx, n=1):
+        """RG.py:230-242.  The reference implementation raises AttributeError on every call (it passes an
+        ndarray to `sym`, quirk Q1); the finite-difference Jacobian itself is out of scope of this path."""
+        raise AttributeError("'numpy.ndarray' object has no attribute 'f'")
+
+    # ------------------------------------------------------------------ RG.py:244-253
+    def norm_int(self, h):
+        f = _f64(h.f).reshape(1, -1)
+        out = xp.empty(1)
+        _lib.check(_lib.lib().rg_norm(self._plan(), 1, f.ctypes.data, WHICH_NORM_INT, out.ctypes.data))
+        return out[0]
+
+    def sym(self, h):
+        h_ = copy.deepcopy(h)
+        f = _f64(h.f)
+        out = xp.empty(self.r_jl)
+        _lib.check(_lib.lib().rg_sym(self._plan(), 1, f.ctypes.data, out.ctypes.data))
+        h_.f = out
+        return h_
+
+    # ------------------------------------------------------------------ RG.py:255-276
+    def generate_1Hamiltonian(self, amps, symmetric=False):
+        f_ = xp.zeros(self.r_jl, dtype=self.Precision)
+        for k, amp in zip(self.K, amps):
+            f_[k] = amp
+        h = Hamiltonian(self.Omega, f_.astype(xp.float64))   # fp32 only rounds the inputs (quirk Q8)
+        h.f[2][self.zero_] = 0.5
+        if symmetric:
+            return self.sym(h)
+        else:
+            return h
+
+    def generate_2Hamiltonians(self, amps):
+        h_list = [self.generate_1Hamiltonian(amp, symmetric=True) for amp in amps]
+        conv = self.converge_batch(h_list)
+        if not conv[0]:
+            warnings.warn('Iterates of H₁ do not converge')
+            h_list[0].error = 3
+        if conv[1]:
+            warnings.warn('Iterates of H₂ do not diverge')
+            h_list[1].error = -3
+        else:
+            h_list[1].error = 0
+        return h_list
+
+    # ------------------------------------------------------------------ RG.py:278-290
+    def converge(self, h):
+        return self.converge_batch([h])[0]
+
+    def converge_batch(self, h_list):
+        """RG.converge on several Hamiltonians in one launch (one CTA each); writes count/error into
+        each h exactly as RG.py:285,288-289 and returns the list of booleans."""
+        n = len(h_list)
+        if n == 0:
+            return []
+        groups = {}
+        for i, h in enumerate(h_list):
+            groups.setdefault(_f64(xp.asarray(h.Omega)).tobytes(), []).append(i)
+        res = [None] * n
+        for key, idx in groups.items():
+            nrm, onu, oms, tab = self._tables(h_list[idx[0]].Omega)
+            f = xp.stack([_f64(h_list[i].f).reshape(-1) for i in idx])
+            conv, count = xp.zeros(len(idx), xp.int32), xp.zeros(len(idx), xp.int32)
+            err = xp.array([h_list[i].error for i in idx], dtype=xp.int32)
+            _lib.check(_lib.lib().rg_converge(self._plan(), tab, len(idx), f.ctypes.data, None, conv.ctypes.data,
+                                              count.ctypes.data, err.ctypes.data, self._stats()))
+            for q, i in enumerate(idx):
+                h_list[i].count = int(count[q])
+                h_list[i].error = int(err[q])
+                res[i] = bool(conv[q])
+        return res
+
+    # ------------------------------------------------------------------ RG.py:292-307
+    def approach(self, h_list, reldist, display=False):
+        h_list_ = copy.deepcopy(h_list)
+        for h in h_list_:
+            h.error = 0
+        while self.norm_int(h_list_[0] - h_list_[1]) > reldist * self.norm(h_list_[0].f):
+            h_mid = (h_list_[0] + h_list_[1]) * 0.5
+            if self.converge(h_mid):
+                h_list_[0] = copy.deepcopy(h_mid)
+            else:
+                h_list_[1] = copy.deepcopy(h_mid)
+            if display:
+                print('\033[90m               [{:.6f}   {:.6f}] \033[00m'.format(2 * h_list_[0].f[self.ModesK[0]], 2 * h_list_[1].f[self.ModesK[0]]))
+        if display:
+            print('\033[96m          ε = {} \033[00m'.format([2 * h_list_[0].f[k] for k in self.K]))
+        h_list_[1].error = 0
+        return h_list_
+
+    # ------------------------------------------------------------------ batched region points (RG_modules.py:121-125)
+    def K_flat(self):
+        n1 = 2 * self.L + 1
+        out = []
+        for k in self.K:
+            k = xp.asarray(k)
+            out.append(int(k[0]) * self._M + int(xp.ravel_multi_index(tuple(xp.mod(k[1:], n1)), self.r_jl[1:])))
+        return xp.array(out, dtype=xp.int32)
+
+    def points(self, amps, conv=None, count=None, err=None):
+        """`point` for a batch: amps[B, len(K)] (host ndarray, pinned torch tensor or CUDA tensor).
+        Returns (conv, count, error) int32 arrays (or fills the supplied host/device buffers)."""
+        if isinstance(amps, xp.ndarray):
+            amps = _f64(amps)
+            n = amps.shape[0]
+        else:
+            n = int(amps.shape[0])
+        nK = len(self.K)
+        own = conv is None
+        if own:
+            conv, count, err = (xp.zeros(n, xp.int32) for _ in range(3))
+        nrm, onu, oms, tab = self._tables(self.Omega)
+        kf = self.K_flat()
+        _lib.check(_lib.lib().rg_region(self._plan(), tab, n, _ptr(amps), kf.ctypes.data, nK, _ptr(conv), _ptr(count),
+                                        _ptr(err), self._stats()))
+        return conv, count, err

@@ -1,0 +1,89 @@
+"""GPU parity of every operator of the hot path against the CPU oracle and the reference goldens.
+All calls go through the C ABI (ctypes) via the rg_b200.RG mirror class."""
+import numpy as np
+import pytest
+
+from conftest import golden, relmax
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-12   # norm-relative (max|a-b|/max|b|); the north_star bar is 1e-10
+
+
+def make(L, J, ct="expm_onestep", **kw):
+    from rg_b200 import RG, make_param_dict
+    return RG(make_param_dict(L=L, J=J, CanonicalTransformation=ct, SaveData=False, **kw))
+
+
+CASES = [("ops_golden_L5J5", 5, 5), ("ops_golden_L10J10", 10, 10), ("ops_golden_L5J5_b", 5, 5)]
+
+
+@pytest.mark.parametrize("name,L,J", CASES)
+def test_elementwise_ops(name, L, J):
+    from rg_b200 import Hamiltonian
+    g = golden(name)
+    c = make(L, J)
+    h0 = c.generate_1Hamiltonian(list(g["amps"]), symmetric=True)
+    assert np.array_equal(h0.f, g["f0"])
+    assert np.array_equal(c.Iminus, g["Iminus"])
+    hg = Hamiltonian(c.Omega, g["op_g"].copy())
+    assert relmax(c.sym(hg).f, g["op_sym_g"]) < 1e-15
+    assert abs(c.norm_int(hg) - g["op_norm_int_g"]) < 1e-13 * abs(g["op_norm_int_g"])
+    for nc in ("sum", "max", "Euclidean", "Analytic"):
+        c2 = make(L, J, NormChoice=nc)
+        assert abs(c2.norm(g["op_g"]) - g["op_norm_" + nc]) <= 1e-13 * abs(g["op_norm_" + nc]), nc
+        c2.close()
+    c.close()
+
+
+@pytest.mark.parametrize("name,L,J", CASES)
+def test_generate_y_liouville_conv(name, L, J):
+    from rg_b200 import Hamiltonian
+    g = golden(name)
+    c = make(L, J)
+    c.Omega_nu = g["op_Omega_nu"].copy()
+    h = Hamiltonian(c.Omega, g["op_f"].copy())
+    y = c.generate_y(h)
+    assert abs(y[0] - g["op_y0"]) <= 1e-15 * abs(g["op_y0"])
+    for k in (1, 2, 3):
+        assert relmax(y[k], g["op_y%d" % k]) < 1e-14, k
+    yg = (g["op_y0"], g["op_y1"], g["op_y2"], g["op_y3"])
+    assert relmax(c.conv_product(yg[1], g["op_g"]), g["op_conv_y1_g"]) < TOL
+    assert relmax(c.conv_product(g["op_g"], g["op_g"]), g["op_conv_g_g"]) < TOL
+    assert relmax(c.liouville(yg, g["op_g"]), g["op_liouville_g"]) < TOL
+    assert relmax(c.liouville(yg, g["op_f"]), g["op_liouville_f"]) < TOL
+    c.close()
+
+
+@pytest.mark.parametrize("name,L,J", CASES)
+def test_expm_onestep_adapt(name, L, J):
+    from rg_b200 import Hamiltonian
+    g = golden(name)
+    c = make(L, J)
+    c.Omega_nu = g["op_Omega_nu"].copy()
+    h = Hamiltonian(c.Omega, g["op_f"].copy())
+    yg = (g["op_y0"], g["op_y1"], g["op_y2"], g["op_y3"])
+    e = c.expm_onestep(h, yg)
+    assert relmax(e.f, g["op_onestep_f"]) < TOL and e.error == int(g["op_onestep_err"])
+    e = c.expm_onestep(h, yg, 0.5)
+    assert relmax(e.f, g["op_onestep_half_f"]) < TOL
+    e = c.expm_adapt(h, yg)
+    assert relmax(e.f, g["op_adapt_f"]) < TOL and e.error == int(g["op_adapt_err"])
+    c.close()
+
+
+@pytest.mark.parametrize("name,L,J", CASES + [("ops_golden_L7J4", 7, 4)])
+@pytest.mark.parametrize("ct", ["expm_onestep", "expm_adapt"])
+def test_rg_map_iterates(name, L, J, ct):
+    """Coefficient arrays after k RG iterates agree with the reference to 1e-10 (norm-relative)."""
+    g = golden(name)
+    c = make(L, J, ct)
+    h = c.generate_1Hamiltonian(list(g["amps"]), symmetric=True)
+    ref = g["rgmap_f_" + ct]
+    for k in range(ref.shape[0]):
+        h = c.rg_map(h)
+        assert relmax(h.f, ref[k]) < 1e-10, (k, relmax(h.f, ref[k]))
+        assert h.error == int(g["rgmap_err_" + ct][k])
+        assert np.array_equal(np.asarray(h.Omega, float), g["rgmap_Omega_" + ct][k])
+        assert np.array_equal(c.Omega_nu, g["rgmap_Omega_nu_" + ct][k])
+    c.close()

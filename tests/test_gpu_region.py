@@ -1,0 +1,70 @@
+"""Region maps (RG_modules.point / compute_region) on the GPU: iteration counts, convergence flags and
+error codes must be bit-exact against maps frozen from the live reference (tests/golden/)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden, GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+def make(L, J, ct, **kw):
+    from rg_b200 import RG, make_param_dict
+    return RG(make_param_dict(L=L, J=J, CanonicalTransformation=ct, SaveData=False, **kw))
+
+
+def run_region(c, g):
+    from rg_b200.rg_modules import region_maps
+    data, info = region_maps(c, g["xs"], g["ys"])
+    return data[:, :, 0], data[:, :, 1], info
+
+
+def check_maps(c, g, allow=0):
+    conv, count, err = run_region(c, g)
+    bad = (conv != g["conv"]) | (count != g["count"]) | (err != g["error"])
+    assert bad.sum() <= allow, ("mismatching points", np.argwhere(bad).tolist(), count[bad].tolist(), g["count"][bad].tolist())
+    return c.last_stats
+
+
+@pytest.mark.parametrize("ct", ["expm_onestep", "expm_adapt"])
+def test_region_L5J5_12x12(ct):
+    """G-A of SURVEY 8(c)."""
+    g = golden("region_L5J5_12x12_" + ct)
+    c = make(5, 5, ct)
+    st = check_maps(c, g)
+    # liouville work executed on the device is within a few % of what the reference executed
+    ref = int(g["liouvilles"].sum())
+    assert abs(st.liouville - ref) <= 0.05 * ref, (st.liouville, ref)
+    assert st.rg_maps == int(g["rg_maps"].sum())
+    c.close()
+
+
+def test_region_L5J5_default_domain():
+    """G-B of SURVEY 8(c): default amplitude domain, mostly diverging points (error 2)."""
+    g = golden("region_L5J5_8x8_default_expm_onestep")
+    c = make(5, 5, "expm_onestep")
+    check_maps(c, g)
+    c.close()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(GOLDEN, "region_L10J10_sub16_expm_onestep.npz")), reason="golden missing")
+def test_region_L10J10_subsample():
+    """G-C: 16x16 strided subsample of BASELINE config 4 (Nxy=256, L=J=10)."""
+    g = golden("region_L10J10_sub16_expm_onestep")
+    c = make(10, 10, "expm_onestep")
+    st = check_maps(c, g)
+    ref = int(g["liouvilles"].sum())
+    assert abs(st.liouville - ref) <= 0.05 * ref, (st.liouville, ref)
+    c.close()
+
+
+def test_point_api_matches_batch():
+    from rg_b200 import point
+    c = make(5, 5, "expm_onestep")
+    g = golden("region_L5J5_12x12_expm_onestep")
+    for iy, ix in ((3, 7), (4, 5), (10, 1), (0, 0)):
+        (cv, cnt), err = point(g["xs"][ix], g["ys"][iy], c)
+        assert (cv, cnt, err) == (int(g["conv"][iy, ix]), int(g["count"][iy, ix]), int(g["error"][iy, ix]))
+    c.close()
