@@ -41,7 +41,7 @@ extern "C" int rg_device_count(int* n) {
 
 // ------------------------------------------------------------------------------------------------ kernels
 struct Job {
-    int mode;  // 0 region (amps), 1 converge (f given), 2 rg_map x n_iter, 3 expm, 4 liouville, 5 generate_y
+    int mode;  // 0 region (amps), 1 converge (f given), 2 rg_map x n_iter, 3 expm, 4 liouville, 5 generate_y, 6 compute_m_s
     int n;
     int sched;  // 0 sparse, 1 dense
     int* ticket;
@@ -57,6 +57,7 @@ struct Job {
     int* conv; int* count; int* err;
     double* f_out; double* y0_out; double* y1_out; double* y2_out; double* y3_out;
     long long* n_liou; long long* n_lie; long long* n_maps;
+    int* m_out; int* s_out; double* norm1_out;   // mode 6
     double* ws_base;
 };
 
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(512, 1) rg_kernel(const int slot, const __grid
         const int item = *sh_item;
         if (item >= job.n) break;
         c.n_liou = 0; c.n_lie = 0;
+        c.rng = 0x243F6A8885A308D3ull ^ ((uint64_t)(item + 1) * 0x9E3779B97F4A7C15ull);
         long long n_maps = 0;
         double* f = fa;
         const int k0 = job.k0 ? job.k0[item] : 0;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(512, 1) rg_kernel(const int slot, const __grid
             }
             __syncthreads();
             sym_and_norms(c, f, true);
-        } else {
+        } else if (job.mode != 6) {
             load_wrapped(P, job.f_in + (size_t)item * P.vecjl, f);
             __syncthreads();
         }
@@ -166,6 +168,21 @@ __global__ void __launch_bounds__(512, 1) rg_kernel(const int slot, const __grid
                 liouville_apply<J>(c, f, dst, a, false);
                 __syncthreads();
                 store_wrapped(P, dst, job.f_out + (size_t)item * P.vecjl);
+            }
+        } else if (job.mode == 6) {
+            // RG.compute_m_s  RG.py:130-150
+            c.Omega_nu = job.Omega_nu;
+            load_wrapped(P, job.y1 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y1 * P.vecjl);
+            load_wrapped(P, job.y2 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y2 * P.vecjl);
+            __syncthreads();
+            build_Y(c, 1.0, 1.0, false);
+            __syncthreads();
+            int m_star; double scale, n1;
+            compute_m_s<J>(c, job.y0[item], m_star, scale, n1);
+            if (threadIdx.x == 0) {
+                job.m_out[item] = m_star;
+                job.s_out[item] = scale < 2147483647.0 ? (int)scale : 2147483647;
+                job.norm1_out[item] = n1;
             }
         } else if (job.mode == 5) {
             c.Omega_nu = job.Omega_nu;
@@ -806,8 +823,23 @@ extern "C" int rg_conv_product(rg_plan* p, int32_t n, const double* f1, const do
 
 extern "C" int rg_compute_m_s(rg_plan* p, int32_t n, const double* y0, const double* y1, const double* y2,
                               const double* Omega_nu, int32_t* m_star, int32_t* scale, double* norm1) {
-    (void)p; (void)n; (void)y0; (void)y1; (void)y2; (void)Omega_nu; (void)m_star; (void)scale; (void)norm1;
-    return fail(-7, "rg_compute_m_s not available in this build");
+    if (!p || n < 0 || !y0 || !y1 || !y2 || !Omega_nu || !m_star || !scale) return fail(-1, "bad argument");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    Job job; memset(&job, 0, sizeof(job));
+    job.mode = 6; job.n = n; job.sched = 1;
+    const size_t vb = sizeof(double) * (size_t)n * p->g.vecjl;
+    int rc; const void* d; void* o;
+    if ((rc = st.in(y0, sizeof(double) * (size_t)n, &d))) return rc; job.y0 = (const double*)d;
+    if ((rc = st.in(y1, vb, &d))) return rc; job.y1 = (const double*)d;
+    if ((rc = st.in(y2, vb, &d))) return rc; job.y2 = (const double*)d;
+    if ((rc = stage_Omega_nu(p, st, Omega_nu, &job.Omega_nu))) return rc;
+    if ((rc = st.outp(m_star, sizeof(int) * (size_t)n, &o))) return rc; job.m_out = (int*)o;
+    if ((rc = st.outp(scale, sizeof(int) * (size_t)n, &o))) return rc; job.s_out = (int*)o;
+    std::vector<double> dummy((size_t)std::max(n, 1));
+    if ((rc = st.outp(norm1 ? norm1 : dummy.data(), sizeof(double) * (size_t)n, &o))) return rc; job.norm1_out = (double*)o;
+    if ((rc = launch_job(p, null_tables(), job, nullptr, st))) return rc;
+    return st.finish();
 }
 
 // ---- host-only schedule introspection (tests replay it in numpy; no device needed)

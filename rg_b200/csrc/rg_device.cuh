@@ -40,7 +40,7 @@ struct DevPlan {
 };
 
 // workspace arrays of one CTA (each vecjl doubles, layout [j][centred nu])
-enum { WS_FA = 0, WS_FB, WS_Y1, WS_Y2, WS_Y3, WS_H1, WS_H2, WS_T0, WS_T1, WS_T2, WS_T3, WS_T4, WS_T5, WS_T6, WS_T7, WS_COUNT };
+enum { WS_FA = 0, WS_FB, WS_Y1, WS_Y2, WS_Y3, WS_H1, WS_H2, WS_T0, WS_T1, WS_T2, WS_T3, WS_T4, WS_T5, WS_T6, WS_T7, WS_T8, WS_COUNT };
 
 // Plans live in constant memory (uniform-datapath loads inside the device functions); a launch names
 // its plan by slot.  Shared-memory pointers are always re-derived from the __shared__ symbol so that
@@ -55,6 +55,7 @@ struct Ctx {
     double* ws;   // this CTA's global workspace
     const double* Omega_nu;  // current Omega.nu, centred, global
     long long n_liou, n_lie;
+    uint64_t rng;  // state of the 1-norm estimator's +-1 columns (seeded per Hamiltonian)
 };
 
 struct Smem {

@@ -1,0 +1,193 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/rg_b200.h declares, the ctypes structs match the C layout, compute calls fail loudly without
+a GPU, and the host-side convolution schedule (rg_debug_schedule) replayed in numpy reproduces the
+oracle's Poisson bracket."""
+import ctypes
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden, relmax
+
+import rg_oracle as ro
+from rg_b200 import _lib
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "rg_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return re.findall(r"^(?:int|void|const char\*)\s+(rg_\w+)\s*\(", src, flags=re.M)
+
+
+def test_library_exports_every_declared_symbol():
+    names = header_functions()
+    assert len(names) >= 18
+    L = _lib.lib()
+    for n in names:
+        assert hasattr(L, n), "librg_b200.so does not export %s" % n
+        assert n in _lib.SIGNATURES, "no ctypes signature for %s" % n
+    assert sorted(names) == sorted(_lib.SIGNATURES)
+
+
+def test_struct_layouts_match_c():
+    prog = r'''
+    #include <stdio.h>
+    #include <stddef.h>
+    #include "rg_b200.h"
+    int main(void) { printf("%zu %zu %zu %zu\n", sizeof(rg_params), sizeof(rg_stats),
+                            offsetof(rg_params, omega0_nu), offsetof(rg_stats, kernel_ms)); return 0; }
+    '''
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(prog)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
+        out = subprocess.check_output([os.path.join(d, "t")]).split()
+    assert int(out[0]) == ctypes.sizeof(_lib.RGParams)
+    assert int(out[1]) == ctypes.sizeof(_lib.RGStats)
+    assert int(out[2]) == _lib.RGParams.omega0_nu.offset
+    assert int(out[3]) == _lib.RGStats.kernel_ms.offset
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device every compute entry point must fail loudly (never fall back to the CPU)."""
+    if _lib.device_count() > 0:
+        pytest.skip("a GPU is visible")
+    from rg_b200 import RG, make_param_dict
+    c = RG(make_param_dict(L=5, J=5, SaveData=False))
+    h = c.generate_1Hamiltonian  # building the host object is fine ...
+    with pytest.raises(_lib.RGError):
+        h([0.01, 0.02], symmetric=True)          # ... but sym() runs on the device
+    with pytest.raises(_lib.RGError):
+        c.norm(np.zeros(c.r_jl))
+    with pytest.raises(_lib.RGError):
+        c.points(np.zeros((4, 2)))
+
+
+def product_imports_no_oracle():
+    for dp, _, fns in os.walk(os.path.join(ROOT, "rg_b200")):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".hpp")):
+                txt = open(os.path.join(dp, fn)).read()
+                assert "rg_oracle" not in txt and "oracle/" not in txt, fn
+
+
+def test_product_never_touches_the_oracle():
+    product_imports_no_oracle()
+
+
+# ------------------------------------------------------------------------------------------ schedule replay
+def fetch_schedule(c, dense):
+    L_ = _lib.lib()
+    nw, ne, ns = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    lane_out, pieces, supp = (ctypes.POINTER(ctypes.c_int32)() for _ in range(3))
+    entries = ctypes.POINTER(ctypes.c_uint32)()
+    im = np.ascontiguousarray(c.Iminus.reshape(-1), dtype=np.uint8)
+    _lib.check(L_.rg_debug_schedule(c.dim, c.L, c.J, im.ctypes.data, int(dense), ctypes.byref(nw), ctypes.byref(lane_out),
+                                    ctypes.byref(pieces), ctypes.byref(ne), ctypes.byref(entries), ctypes.byref(ns),
+                                    ctypes.byref(supp)))
+    M = (2 * c.L + 1) ** c.dim
+    out = dict(nw=nw.value, ns=ns.value,
+               lane_out=np.ctypeslib.as_array(lane_out, (nw.value * 32,)).copy(),
+               pieces=np.ctypeslib.as_array(pieces, (nw.value * 2, 4)).copy(),
+               entries=np.ctypeslib.as_array(entries, (max(ne.value, 1), 2)).copy()[:ne.value],
+               supp=np.ctypeslib.as_array(supp, (M,)).copy())
+    for p in (lane_out, pieces, entries, supp):
+        L_.rg_debug_free(p)
+    return out
+
+
+def centred(c, a):
+    """reference layout [j][wrapped...] -> [centred flat nu][j]"""
+    L = c.L
+    a = np.roll(a, c.dim * (L,), axis=tuple(range(1, c.dim + 1)))
+    return a.reshape(c.J + 1, -1).T.copy()
+
+
+def replay(c, sched, y1, y2, g, Omega_nu, dense):
+    """Execute the schedule exactly as conv_all does (lane = output mode, warp-uniform nu1 list)."""
+    L, J, dim, n1 = c.L, c.J, c.dim, 2 * c.L + 1
+    M = n1 ** dim
+    Y1, Y2, G = centred(c, y1), centred(c, y2), centred(c, g)
+    Om = centred(c, np.broadcast_to(Omega_nu, (c.J + 1,) + Omega_nu.shape[1:]))[:, 0]
+    B1 = Om[:, None] * G                                   # Omega_nu * g
+    B2 = np.zeros_like(G)
+    B2[:, :J] = G[:, 1:] * np.arange(1, J + 1)             # dA g
+    B1 = np.vstack([B1, np.zeros((1, J + 1))])             # the all-zero record
+    B2 = np.vstack([B2, np.zeros((1, J + 1))])
+    rec_of = sched["supp"]
+    nu_of_rec = np.zeros(sched["ns"], dtype=int)
+    nu_of_rec[rec_of[rec_of >= 0]] = np.nonzero(rec_of >= 0)[0]
+    strides = [n1 ** (dim - 1 - d) for d in range(dim)]
+    coords = np.stack([(np.arange(M) // strides[d]) % n1 for d in range(dim)], axis=1)   # biased coords
+    out = np.zeros((M, J + 1))
+    written = np.zeros(M, dtype=int)
+    for w in range(sched["nw"]):
+        for q in range(2):
+            box, b, e, mode = sched["pieces"][w * 2 + q]
+            if mode == 0:
+                continue
+            lanes = sched["lane_out"][box * 32:(box + 1) * 32]
+            acc = np.zeros((32, J + 1))
+            for ent in sched["entries"][b:e]:
+                ec = [(int(ent[0]) >> (8 * d)) & 0xff for d in range(dim)]
+                jm, rec = int(ent[1]) & 0xff, int(ent[1]) >> 8
+                nu1 = nu_of_rec[rec]
+                assert list(coords[nu1]) == ec
+                for l, nu in enumerate(lanes):
+                    if nu < 0:
+                        continue
+                    u = coords[nu] - coords[nu1] + L
+                    gi = int((u * strides).sum()) if ((u >= 0) & (u <= 2 * L)).all() else M
+                    for j1 in range(J + 1):
+                        if j1 + 1 < jm and j1 <= J:     # y1[j1] = (j1+1) y[j1+1]
+                            a = Y1[nu1, j1]
+                            acc[l, j1:J + 1] += a * B1[gi, :J + 1 - j1]
+                        if j1 < jm:
+                            a = Y2[nu1, j1]
+                            acc[l, j1:J + 1] -= a * B2[gi, :J + 1 - j1]
+            for l, nu in enumerate(lanes):
+                if nu >= 0:
+                    out[nu] += acc[l]
+                    written[nu] += (mode == 1)
+    assert (written == 1).all(), "every output mode must have exactly one primary piece"
+    # back to the reference layout
+    res = out.T.reshape((J + 1,) + dim * (n1,))
+    return np.roll(res, dim * (-L,), axis=tuple(range(1, dim + 1)))
+
+
+@pytest.mark.parametrize("name,over,dense", [("ops_golden_L5J5", dict(L=5, J=5), False),
+                                             ("ops_golden_L5J5", dict(L=5, J=5), True),
+                                             ("ops_spiral_L4J4", dict(L=4, J=4, torus="spiral"), False)])
+def test_schedule_replay_matches_oracle(name, over, dense):
+    g = golden(name)
+    c = ro.OracleRG(ro.default_params(**over))
+    c.Omega_nu = g["op_Omega_nu"].copy()
+    sched = fetch_schedule(c, dense)
+    assert sched["nw"] * 32 >= c.M
+    lanes = sched["lane_out"][sched["lane_out"] >= 0]
+    assert sorted(lanes) == list(range(c.M)), "every output mode owned by exactly one lane"
+    got = replay(c, sched, g["op_y1"], g["op_y2"], g["op_g"], g["op_Omega_nu"], dense)
+    yg = (0.0, g["op_y1"], g["op_y2"], g["op_y3"])
+    want = c.liouville(yg, g["op_g"])          # y0 = 0: only the two convolutions
+    assert relmax(got, want) < 1e-13
+
+
+def test_schedule_geometry_config4():
+    """The L=J=10 schedule: 14 warps, I^- support of 252 modes, every box in at most two pieces."""
+    c = ro.OracleRG(ro.default_params(L=10, J=10))
+    s = fetch_schedule(c, False)
+    assert s["nw"] == 14 and s["ns"] == 252
+    for box in range(s["nw"]):
+        n_pieces = sum(1 for p in s["pieces"] if p[3] != 0 and p[0] == box)
+        assert 1 <= n_pieces <= 2
+    # pieces are balanced to within 10% of the mean cost (cost ~ entries here, jm is mostly J+1)
+    cost = np.zeros(s["nw"])
+    for w in range(s["nw"]):
+        for q in range(2):
+            b, e, mode = s["pieces"][w * 2 + q][1:]
+            if mode:
+                cost[w] += e - b
+    assert cost.max() <= 1.35 * cost.mean()

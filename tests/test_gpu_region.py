@@ -28,7 +28,7 @@ def check_maps(c, g, allow=0):
     return c.last_stats
 
 
-@pytest.mark.parametrize("ct", ["expm_onestep", "expm_adapt"])
+@pytest.mark.parametrize("ct", ["expm_onestep", "expm_adapt", "expm_multiply"])
 def test_region_L5J5_12x12(ct):
     """G-A of SURVEY 8(c)."""
     g = golden("region_L5J5_12x12_" + ct)
@@ -36,7 +36,8 @@ def test_region_L5J5_12x12(ct):
     st = check_maps(c, g)
     # liouville work executed on the device is within a few % of what the reference executed
     ref = int(g["liouvilles"].sum())
-    assert abs(st.liouville - ref) <= 0.05 * ref, (st.liouville, ref)
+    tol = 0.05 if ct != "expm_multiply" else 0.5     # the 1-norm estimator's call count is RNG dependent
+    assert abs(st.liouville - ref) <= tol * ref, (st.liouville, ref)
     assert st.rg_maps == int(g["rg_maps"].sum())
     c.close()
 

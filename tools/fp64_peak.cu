@@ -26,6 +26,30 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
     if (s == 12345.678) out[0] = s;
 }
 
+// the convolution's instruction mix: acc[i+j] += a[i]*b[j] with three distinct register operands per DFMA
+template <int NA, int NB>
+__global__ void __launch_bounds__(512) dfma3_kernel(double* out, const double* in, int iters) {
+    double acc[NA + NB], a[NA], b[NB];
+#pragma unroll
+    for (int i = 0; i < NA + NB; ++i) acc[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NA; ++i) a[i] = in[(threadIdx.x + i) & 1023];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) b[i] = in[(threadIdx.x * 3 + i) & 1023];
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < NA; ++i)
+#pragma unroll
+            for (int j = 0; j < NB; ++j) acc[i + j] = fma(a[i], b[j], acc[i + j]);
+#pragma unroll
+        for (int i = 0; i < NA; ++i) a[i] += 1e-9;   // keep the loop from being hoisted
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < NA + NB; ++i) s += acc[i];
+    if (s == 12345.678) out[0] = s;
+}
+
 template <int NACC>
 __global__ void __launch_bounds__(256) dmma_kernel(double* out, int iters, double a0, double b0) {
     double c[NACC][2];
@@ -104,6 +128,17 @@ int main() {
         ms = time_ms([&] { dfma_kernel<NCH><<<blocks, 128>>>(d, iters, 1.0000001, 1e-9); }, 5);
         flops = 2.0 * NCH * iters * 128.0 * blocks;
         printf(", \"dfma_tflops_4warps_per_sm\": %.3f", flops / ms * 1e-9);
+    }
+    {   // three-operand DFMA (polynomial product, the convolution's inner loop), 448 and 128 threads per SM
+        double* din; CK(cudaMalloc(&din, 1024 * 8)); CK(cudaMemset(din, 0, 1024 * 8));
+        const int it3 = 2000;
+        int blocks = sms;
+        float ms = time_ms([&] { dfma3_kernel<11, 11><<<blocks, 448>>>(d, din, it3); }, 5);
+        double flops = 2.0 * (121 + 11) * it3 * 448.0 * blocks;
+        printf(", \"dfma_3operand_tflops_14warps_per_sm\": %.3f", flops / ms * 1e-9);
+        ms = time_ms([&] { dfma3_kernel<11, 11><<<blocks, 128>>>(d, din, it3); }, 5);
+        flops = 2.0 * (121 + 11) * it3 * 128.0 * blocks;
+        printf(", \"dfma_3operand_tflops_4warps_per_sm\": %.3f", flops / ms * 1e-9);
     }
     {   // DMMA m8n8k4: 256 MAC per warp instruction
         const int NACC = 8; int blocks = sms * 4;
