@@ -58,9 +58,9 @@ SIGNATURES = {
     "rg_reindex_rescale": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, vp]),
     "rg_compute_m_s": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp, vp, vp, vp]),
     "rg_debug_schedule": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, ctypes.c_int32,
-                                         c_int_p, ctypes.POINTER(c_int_p), ctypes.POINTER(c_int_p), c_int_p,
+                                         c_int_p, c_int_p, ctypes.POINTER(c_int_p), ctypes.POINTER(c_int_p), c_int_p,
                                          ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), c_int_p,
-                                         ctypes.POINTER(c_int_p)]),
+                                         ctypes.POINTER(c_int_p), ctypes.POINTER(ctypes.c_int64)]),
     "rg_debug_free": (None, [vp]),
 }
 

@@ -11,11 +11,12 @@
 
 namespace rgdev {
 
+#define RG_MAXP 4   // pieces per warp (rgplan::MAXP)
 struct Sched {
-    int n_warps, n_support;
-    const int* lane_out;         // [NW*32] centred mode of each lane, -1 idle
-    const uint32_t* lane_coord;  // [NW*32] packed biased coords
-    const int4* pieces;          // [NW*2] {box_warp, begin, end, mode}
+    int n_warps, n_boxes, n_support, max_rank, half;
+    const int* lane_out;         // [NB*32] centred mode of each lane, -1 idle
+    const uint32_t* lane_coord;  // [NB*32] packed biased coords
+    const int4* pieces;          // [NW*RG_MAXP] {box, begin, end, rank}; box = -1 unused; heads first
     const uint2* entries;        // {packed coords of nu1, (rec<<8)|jm}
     const int* supp_rec;         // [M] record of centred mode or -1
 };
@@ -36,7 +37,8 @@ struct DevPlan {
     const int* c2w;           // [M] centred -> wrapped index
     const double* theta;
     int n_theta;
-    Sched sched[2];           // 0: I^- support (fused path), 1: dense (caller-supplied y)
+    Sched sched[3];           // 0: I^- support, all modes; 1: dense (caller-supplied y); 2: I^- support, half
+                              // space only (exactly symmetric operands: out[-nu] = out[nu])
 };
 
 // workspace arrays of one CTA (each vecjl doubles, layout [j][centred nu])
@@ -51,7 +53,8 @@ extern __shared__ double2 smem_dyn[];
 
 struct Ctx {
     int slot;     // index into c_plan
-    int sidx;     // schedule index (0 sparse, 1 dense)
+    int sidx;     // schedule index (0 sparse, 1 dense, 2 sparse half-space)
+    int symm;     // 1 while the coefficient array is exactly symmetric under nu -> -nu (after RG.sym)
     double* ws;   // this CTA's global workspace
     const double* Omega_nu;  // current Omega.nu, centred, global
     long long n_liou, n_lie;
@@ -190,6 +193,9 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box_warp, int e_beg
 }
 
 // out[nu][j] = conv(dA y, Omega g) - conv(Omega y, dA g)  (G, Y in shared memory).  Ends with a barrier.
+// Every warp owns up to RG_MAXP pieces of the boxes' source lists: heads (rank 0) are stored as they
+// finish, the single continuation a warp may hold (rank r > 0) is added in phase r -- a fixed order, so
+// the result does not depend on timing.  On the half-space schedule only modes nu <= 0 are produced.
 template <int J>
 __device__ __noinline__ void conv_all(Ctx& c) {
     constexpr int JP = J + 1;
@@ -197,26 +203,33 @@ __device__ __noinline__ void conv_all(Ctx& c) {
     double* const out = smem_view(RG_PLAN(c), S).out;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double acc[JP];
-    const int4 p0 = S.pieces[w * 2 + 0];
-    const int4 p1 = S.pieces[w * 2 + 1];
-    if (p0.w == 1) {
-        conv_piece<J>(c, p0.x, p0.y, p0.z, acc);
-        const int nu = S.lane_out[p0.x * 32 + lane];
-        if (nu >= 0) {
+    int4 held = make_int4(-1, 0, 0, 0);
+    if (w < S.n_warps) {
+#pragma unroll 1
+        for (int q = 0; q < RG_MAXP; ++q) {
+            const int4 p = S.pieces[w * RG_MAXP + q];
+            if (p.x < 0) continue;
+            if (p.w > 0) { held = p; continue; }
+            conv_piece<J>(c, p.x, p.y, p.z, acc);
+            const int nu = S.lane_out[p.x * 32 + lane];
+            if (nu >= 0) {
 #pragma unroll
-            for (int j = 0; j < JP; ++j) out[nu * JP + j] = acc[j];
+                for (int j = 0; j < JP; ++j) out[nu * JP + j] = acc[j];
+            }
         }
-    }
-    if (p1.w == 2) conv_piece<J>(c, p1.x, p1.y, p1.z, acc);
-    __syncthreads();
-    if (p1.w == 2) {
-        const int nu = S.lane_out[p1.x * 32 + lane];
-        if (nu >= 0) {
-#pragma unroll
-            for (int j = 0; j < JP; ++j) out[nu * JP + j] += acc[j];
-        }
+        if (held.x >= 0) conv_piece<J>(c, held.x, held.y, held.z, acc);
     }
     __syncthreads();
+    for (int r = 1; r <= S.max_rank; ++r) {
+        if (held.x >= 0 && held.w == r) {
+            const int nu = S.lane_out[held.x * 32 + lane];
+            if (nu >= 0) {
+#pragma unroll
+                for (int j = 0; j < JP; ++j) out[nu * JP + j] += acc[j];
+            }
+        }
+        __syncthreads();
+    }
     c.n_liou++;
 }
 
@@ -260,20 +273,25 @@ __device__ __noinline__ void build_Y(const Ctx& c, double step, double divisor, 
 }
 
 // One series term: sh = [y3 +] (a0*dA g + conv) [/ m]; f += sh; G <- records of sh.
-// Returns (norm(sh), norm(f)).  Thread <-> mode nu.
+// Returns (norm(sh), norm(f)).  Thread <-> mode nu.  On the half-space schedule the thread of nu <= 0 also
+// writes the mirror mode -nu (sh, f are exactly symmetric, Omega_nu exactly antisymmetric).
 template <int J>
 __device__ __noinline__ double2 series_epilogue(Ctx& c, double* __restrict__ f, double a0, bool first, double y3mul,
-                                                   double y3div, bool use_div, double m) {
+                                                double y3div, bool use_div, double m) {
     constexpr int JP = J + 1;
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M, type = P.norm_choice;
+    const bool half = RG_SCHED(c).half != 0;
+    const int nmax = half ? (M + 1) / 2 : M;
     const double* y3 = c.ws + (size_t)WS_Y3 * P.vecjl;
     const Smem sm = smem_view(P, RG_SCHED(c));
     double ps = 0.0, pf = 0.0;
-    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+    for (int nu = threadIdx.x; nu < nmax; nu += blockDim.x) {
         double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
         const double om = c.Omega_nu[nu];
         const double w = (type == 3) ? P.normw[nu] : 1.0;
+        const int mu = M - 1 - nu;
+        const bool twin = half && (mu != nu);
         double sh[JP];
 #pragma unroll
         for (int j = 0; j < JP; ++j) {
@@ -291,11 +309,24 @@ __device__ __noinline__ double2 series_epilogue(Ctx& c, double* __restrict__ f, 
             f[j * M + nu] = fn;
             norm_acc(type, ps, v, w);
             norm_acc(type, pf, fn, w);
+            if (twin) {
+                f[j * M + mu] = fn;
+                norm_acc(type, ps, v, w);
+                norm_acc(type, pf, fn, w);
+            }
         }
 #pragma unroll
         for (int j = 0; j < JP; ++j) {
             r[P.off2 + j] = om * sh[j];
             if (j < J) r[j] = sh[j + 1] * (double)(j + 1);
+        }
+        if (twin) {
+            double* r2 = reinterpret_cast<double*>(sm.G + mu * P.rec_units);
+#pragma unroll
+            for (int j = 0; j < JP; ++j) {
+                r2[P.off2 + j] = -(om * sh[j]);
+                if (j < J) r2[j] = sh[j + 1] * (double)(j + 1);
+            }
         }
     }
     return block_reduce2(sm.red, type, ps, pf);
@@ -313,6 +344,8 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
     const double tol = 1.1102230246251565e-16;
     const double a0 = use_div ? a_unscaled / divisor : a_unscaled * step;
     int err = 0;
+    const int sidx_saved = c.sidx;
+    if (c.sidx == 0 && c.symm) c.sidx = 2;   // exactly symmetric f and antisymmetric y: compute nu <= 0 only
     build_Y(c, step, divisor, use_div);
     build_G(c, f);
     __syncthreads();
@@ -328,6 +361,7 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
         c1 = c2;
         if (m >= P.max_series) { err = 1; break; }  // safety: the reference would spin (quirk Q6)
     }
+    c.sidx = sidx_saved;
     return err;
 }
 
@@ -418,10 +452,11 @@ __device__ __noinline__ double generate_y(const Ctx& c, const double* __restrict
 }
 
 // RG.sym (RG.py:249-253) in place, fused with the I^- norm (RG.py:217-218,221) and norm_int (RG.py:244-247)
-__device__ __noinline__ double2 sym_and_norms(const Ctx& c, double* f, bool do_sym) {
+__device__ __noinline__ double2 sym_and_norms(Ctx& c, double* f, bool do_sym) {
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M, type = P.norm_choice, c0 = (M - 1) / 2;
     double pim = 0.0, pint = 0.0;
+    int asym = 0;
     for (int nu = threadIdx.x; nu <= c0; nu += blockDim.x) {
         const int mu = M - 1 - nu;
         const unsigned mk_a = P.mask[nu], mk_b = P.mask[mu];
@@ -435,6 +470,7 @@ __device__ __noinline__ double2 sym_and_norms(const Ctx& c, double* f, bool do_s
                 f[j * M + nu] = a;
                 if (mu != nu) f[j * M + mu] = b;
             }
+            asym |= !(a == b);
             if ((mk_a >> j) & 1u) norm_acc(type, pim, a, wa);
             if (nu != c0) {
                 if ((mk_b >> j) & 1u) norm_acc(type, pim, b, wb);
@@ -443,6 +479,7 @@ __device__ __noinline__ double2 sym_and_norms(const Ctx& c, double* f, bool do_s
             }
         }
     }
+    c.symm = __syncthreads_or(asym) ? 0 : 1;
     return block_reduce2(smem_view(P, RG_SCHED(c)).red, type, pim, pint);
 }
 

@@ -61,69 +61,76 @@ inline int taylor_fma(int jm, int J) {
     return c;
 }
 
-struct Piece { int box_warp, begin, end, mode; };  // mode: 0 none, 1 store, 2 add (after barrier)
+struct Piece { int box, begin, end, rank; };  // rank: position of the piece within its box's list (0 = head)
+
+constexpr int MAXP = 4;  // pieces per warp: any number of heads (rank 0) up to MAXP-1, at most one continuation
 
 struct Schedule {
-    int n_warps = 0;
+    int n_warps = 0;    // warps per CTA (pieces are dealt to these)
+    int n_boxes = 0;    // groups of <= 32 output modes
     int n_support = 0;
-    std::vector<int32_t> lane_out;     // [NW*32] centred mode index or -1
-    std::vector<uint32_t> lane_coord;  // [NW*32] packed biased coords (0xFFFFFFFF idle)
-    std::vector<Piece> pieces;         // [NW*2]
+    int max_rank = 0;
+    bool half = false;  // outputs restricted to the half space nu <= 0 (exactly symmetric operands)
+    std::vector<int32_t> lane_out;     // [NB*32] centred mode index or -1
+    std::vector<uint32_t> lane_coord;  // [NB*32] packed biased coords (0xFFFFFFFF idle)
+    std::vector<Piece> pieces;         // [NW*MAXP], box = -1 for unused slots; heads first, continuation last
     std::vector<uint32_t> entries;     // [n*2]: {packed biased coords of nu1, (rec<<8)|jm}
     std::vector<int32_t> supp_rec;     // [M] record index of centred nu1, -1 if not in support
     std::vector<uint8_t> jm;           // [M] 1 + highest I^- level (0 = not in support)
     int64_t fma_useful = 0;            // per liouville, in-range & structurally non-zero
     int64_t fma_executed = 0;          // per liouville, 32 lanes x list cost
+    int64_t cost_max = 0, cost_total = 0;  // per-warp list cost (balance = total / (n_warps * max))
 };
 
-// mask[c] = bit j set iff (j, nu_c) in I^- (centred order).  dense: every mode, every level.
-inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& mask, bool dense) {
+// mask[c] = bit j set iff (j, nu_c) in I^- (centred order).  dense: every mode, every level (jm = J+2 so
+// that the y1[J] term of a caller-supplied generator is kept).  half: only modes c <= centre are computed.
+inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& mask, bool dense, bool half, int n_warps) {
     Schedule s;
-    const int M = g.M, L = g.L, J = g.J;
+    const int M = g.M, L = g.L, J = g.J, c0 = (M - 1) / 2;
+    s.half = half;
     s.jm.assign(M, 0);
     s.supp_rec.assign(M, -1);
     for (int c = 0; c < M; ++c) {
         int jm = 0;
-        if (dense) jm = g.JP;
+        if (dense) jm = g.JP + 1;
         else { uint16_t m = mask[c]; while (m) { ++jm; m >>= 1; } }
         s.jm[c] = (uint8_t)jm;
         if (jm > 0) s.supp_rec[c] = s.n_support++;
     }
-    // ---- output order: compact boxes, chunked by 32
-    int box[4] = {1, 1, 1, 1};
-    if (g.dim == 1) { box[0] = 32; }
-    else if (g.dim == 2) { box[0] = 4; box[1] = 8; }
-    else if (g.dim == 3) { box[0] = 2; box[1] = 4; box[2] = 4; }
-    else { box[g.dim - 1] = 8; box[g.dim - 2] = 4; }
-    std::vector<int> order(M);
-    std::iota(order.begin(), order.end(), 0);
+    // ---- output order: (column group of 8 along the last axis, leading axes, column).  A quarter-warp then
+    // gathers 8 records whose indices are distinct mod 8 -> conflict-free LDS.128 with an odd record stride.
+    std::vector<int> order;
+    for (int c = 0; c < M; ++c) if (!half || c <= c0) order.push_back(c);
+    const int last = g.dim - 1;
     auto key = [&](int c) {
         int v[4]; g.coords(c, v);
-        uint64_t k = 0;
-        for (int d = 0; d < g.dim; ++d) k = k * 64 + (uint64_t)(v[d] / box[d]);
-        for (int d = 0; d < g.dim; ++d) k = k * 64 + (uint64_t)(v[d] % box[d]);
-        return k;
+        uint64_t k = (uint64_t)(v[last] / 8);
+        for (int d = 0; d < last; ++d) k = k * 128 + (uint64_t)v[d];
+        return k * 128 + (uint64_t)v[last];
     };
     std::sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
-    const int NW = (M + 31) / 32;
-    s.n_warps = NW;
-    s.lane_out.assign(NW * 32, -1);
-    s.lane_coord.assign(NW * 32, 0xFFFFFFFFu);
-    for (int i = 0; i < M; ++i) {
+    const int NO = (int)order.size();
+    const int NB = (NO + 31) / 32;
+    s.n_boxes = NB;
+    s.n_warps = n_warps > 0 ? n_warps : NB;
+    const int NW = s.n_warps;
+    s.lane_out.assign(NB * 32, -1);
+    s.lane_coord.assign(NB * 32, 0xFFFFFFFFu);
+    for (int i = 0; i < NO; ++i) {
         s.lane_out[i] = order[i];
         int v[4]; g.coords(order[i], v);
         s.lane_coord[i] = g.pack(v);
     }
-    // ---- per-warp union lists
-    std::vector<std::vector<int>> lists(NW);
-    std::vector<int64_t> cost(NW, 0);
-    for (int w = 0; w < NW; ++w) {
+    // ---- per-box union lists
+    std::vector<std::vector<int>> lists(NB);
+    int64_t total = 0;
+    for (int b = 0; b < NB; ++b) {
         for (int c1 = 0; c1 < M; ++c1) {
             if (s.jm[c1] == 0) continue;
             int v1[4]; g.coords(c1, v1);
             int nvalid = 0;
             for (int l = 0; l < 32; ++l) {
-                int co = s.lane_out[w * 32 + l];
+                int co = s.lane_out[b * 32 + l];
                 if (co < 0) continue;
                 int v[4]; g.coords(co, v);
                 bool ok = true;
@@ -131,50 +138,55 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
                 nvalid += ok;
             }
             if (nvalid) {
-                lists[w].push_back(c1);
-                int t = taylor_fma(s.jm[c1], J);
-                cost[w] += t;
+                lists[b].push_back(c1);
+                int t = taylor_fma(std::min<int>(s.jm[c1], g.JP), J) + (s.jm[c1] > g.JP ? 1 : 0);
+                total += t;
                 s.fma_useful += (int64_t)nvalid * t;
                 s.fma_executed += 32LL * t;
             }
         }
     }
-    // ---- balance: pair heaviest with lightest, move the tail of the heavy list to the light warp
-    std::vector<int> byc(NW);
-    std::iota(byc.begin(), byc.end(), 0);
-    std::sort(byc.begin(), byc.end(), [&](int a, int b) { return cost[a] > cost[b]; });
-    std::vector<int> give_to(NW, -1), split_at(NW, -1);
-    for (int i = 0; i < NW / 2; ++i) {
-        int h = byc[i], l = byc[NW - 1 - i];
-        if (cost[h] <= cost[l]) continue;
-        int64_t move = (cost[h] - cost[l]) / 2, acc = 0;
-        int k = (int)lists[h].size();
-        while (k > 0) {
-            int t = taylor_fma(s.jm[lists[h][k - 1]], J);
-            if (acc + t > move) break;
-            acc += t; --k;
-        }
-        if (k < (int)lists[h].size()) { give_to[h] = l; split_at[h] = k; }
+    // ---- deal the concatenated lists to the warps in equal-cost segments.  A warp's segment starts with at
+    // most one continuation of a box (rank > 0) followed by heads of later boxes (rank 0).
+    s.pieces.assign(NW * MAXP, Piece{-1, 0, 0, 0});
+    std::vector<int> npieces(NW, 0);
+    std::vector<int64_t> wcost(NW, 0);
+    auto tcost = [&](int c1) { return (int64_t)taylor_fma(std::min<int>(s.jm[c1], g.JP), J) + (s.jm[c1] > g.JP ? 1 : 0); };
+    int w = 0;
+    int64_t acc = 0;
+    for (int b = 0; b < NB; ++b) {
+        int rank = 0;
+        size_t k = 0;
+        do {
+            // open a piece of box b on warp w
+            while (w < NW - 1 && (npieces[w] >= MAXP || (rank > 0 && npieces[w] > 0) ||
+                                  acc * NW >= total * (int64_t)(w + 1))) ++w;
+            Piece pc{b, (int)s.entries.size() / 2, 0, rank};
+            while (k < lists[b].size()) {
+                const int c1 = lists[b][k];
+                if (w < NW - 1 && acc * NW >= total * (int64_t)(w + 1) && (int)s.entries.size() / 2 > pc.begin) break;
+                int v1[4]; g.coords(c1, v1);
+                s.entries.push_back(g.pack(v1));
+                s.entries.push_back(((uint32_t)s.supp_rec[c1] << 8) | s.jm[c1]);
+                acc += tcost(c1); wcost[w] += tcost(c1);
+                ++k;
+            }
+            pc.end = (int)s.entries.size() / 2;
+            // heads first, the continuation (if any) last
+            if (rank == 0) {
+                int q = npieces[w];
+                if (q > 0 && s.pieces[w * MAXP + q - 1].rank > 0) { s.pieces[w * MAXP + q] = s.pieces[w * MAXP + q - 1]; s.pieces[w * MAXP + q - 1] = pc; }
+                else s.pieces[w * MAXP + q] = pc;
+            } else {
+                s.pieces[w * MAXP + npieces[w]] = pc;
+            }
+            ++npieces[w];
+            s.max_rank = std::max(s.max_rank, rank);
+            ++rank;
+        } while (k < lists[b].size());
     }
-    s.pieces.assign(NW * 2, Piece{0, 0, 0, 0});
-    auto emit = [&](int c1) {
-        int v1[4]; g.coords(c1, v1);
-        s.entries.push_back(g.pack(v1));
-        s.entries.push_back(((uint32_t)s.supp_rec[c1] << 8) | s.jm[c1]);
-    };
-    for (int w = 0; w < NW; ++w) {
-        int kend = split_at[w] >= 0 ? split_at[w] : (int)lists[w].size();
-        int b = (int)s.entries.size() / 2;
-        for (int k = 0; k < kend; ++k) emit(lists[w][k]);
-        s.pieces[w * 2 + 0] = Piece{w, b, (int)s.entries.size() / 2, 1};
-    }
-    for (int h = 0; h < NW; ++h) {
-        if (give_to[h] < 0) continue;
-        int l = give_to[h];
-        int b = (int)s.entries.size() / 2;
-        for (int k = split_at[h]; k < (int)lists[h].size(); ++k) emit(lists[h][k]);
-        s.pieces[l * 2 + 1] = Piece{h, b, (int)s.entries.size() / 2, 2};
-    }
+    for (int i = 0; i < NW; ++i) { s.cost_max = std::max(s.cost_max, wcost[i]); }
+    s.cost_total = total;
     return s;
 }
 

@@ -79,19 +79,24 @@ def test_product_never_touches_the_oracle():
 
 
 # ------------------------------------------------------------------------------------------ schedule replay
-def fetch_schedule(c, dense):
+MAXP = 4
+
+
+def fetch_schedule(c, mode):
+    """mode: 0 sparse (I^- support), 1 dense, 2 sparse half-space."""
     L_ = _lib.lib()
-    nw, ne, ns = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+    nw, nb, ne, ns = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
     lane_out, pieces, supp = (ctypes.POINTER(ctypes.c_int32)() for _ in range(3))
     entries = ctypes.POINTER(ctypes.c_uint32)()
+    cost = (ctypes.c_int64 * 4)()
     im = np.ascontiguousarray(c.Iminus.reshape(-1), dtype=np.uint8)
-    _lib.check(L_.rg_debug_schedule(c.dim, c.L, c.J, im.ctypes.data, int(dense), ctypes.byref(nw), ctypes.byref(lane_out),
-                                    ctypes.byref(pieces), ctypes.byref(ne), ctypes.byref(entries), ctypes.byref(ns),
-                                    ctypes.byref(supp)))
+    _lib.check(L_.rg_debug_schedule(c.dim, c.L, c.J, im.ctypes.data, int(mode), ctypes.byref(nw), ctypes.byref(nb),
+                                    ctypes.byref(lane_out), ctypes.byref(pieces), ctypes.byref(ne), ctypes.byref(entries),
+                                    ctypes.byref(ns), ctypes.byref(supp), cost))
     M = (2 * c.L + 1) ** c.dim
-    out = dict(nw=nw.value, ns=ns.value,
-               lane_out=np.ctypeslib.as_array(lane_out, (nw.value * 32,)).copy(),
-               pieces=np.ctypeslib.as_array(pieces, (nw.value * 2, 4)).copy(),
+    out = dict(nw=nw.value, nb=nb.value, ns=ns.value, cost=list(cost),
+               lane_out=np.ctypeslib.as_array(lane_out, (nb.value * 32,)).copy(),
+               pieces=np.ctypeslib.as_array(pieces, (nw.value * MAXP, 4)).copy(),
                entries=np.ctypeslib.as_array(entries, (max(ne.value, 1), 2)).copy()[:ne.value],
                supp=np.ctypeslib.as_array(supp, (M,)).copy())
     for p in (lane_out, pieces, entries, supp):
@@ -106,7 +111,7 @@ def centred(c, a):
     return a.reshape(c.J + 1, -1).T.copy()
 
 
-def replay(c, sched, y1, y2, g, Omega_nu, dense):
+def replay(c, sched, y1, y2, g, Omega_nu):
     """Execute the schedule exactly as conv_all does (lane = output mode, warp-uniform nu1 list)."""
     L, J, dim, n1 = c.L, c.J, c.dim, 2 * c.L + 1
     M = n1 ** dim
@@ -125,10 +130,13 @@ def replay(c, sched, y1, y2, g, Omega_nu, dense):
     out = np.zeros((M, J + 1))
     written = np.zeros(M, dtype=int)
     for w in range(sched["nw"]):
-        for q in range(2):
-            box, b, e, mode = sched["pieces"][w * 2 + q]
-            if mode == 0:
+        seen_cont = False
+        for q in range(MAXP):
+            box, b, e, rank = sched["pieces"][w * MAXP + q]
+            if box < 0:
                 continue
+            assert not seen_cont, "a continuation must be the last piece of its warp"
+            seen_cont = rank > 0
             lanes = sched["lane_out"][box * 32:(box + 1) * 32]
             acc = np.zeros((32, J + 1))
             for ent in sched["entries"][b:e]:
@@ -142,7 +150,7 @@ def replay(c, sched, y1, y2, g, Omega_nu, dense):
                     u = coords[nu] - coords[nu1] + L
                     gi = int((u * strides).sum()) if ((u >= 0) & (u <= 2 * L)).all() else M
                     for j1 in range(J + 1):
-                        if j1 + 1 < jm and j1 <= J:     # y1[j1] = (j1+1) y[j1+1]
+                        if j1 + 1 < jm:                  # y1[j1] = (j1+1) y[j1+1]; jm = J+2 keeps a caller's y1[J]
                             a = Y1[nu1, j1]
                             acc[l, j1:J + 1] += a * B1[gi, :J + 1 - j1]
                         if j1 < jm:
@@ -151,43 +159,50 @@ def replay(c, sched, y1, y2, g, Omega_nu, dense):
             for l, nu in enumerate(lanes):
                 if nu >= 0:
                     out[nu] += acc[l]
-                    written[nu] += (mode == 1)
-    assert (written == 1).all(), "every output mode must have exactly one primary piece"
+                    written[nu] += (rank == 0)
+    owned = np.zeros(M, dtype=int)
+    owned[sched["lane_out"][sched["lane_out"] >= 0]] = 1
+    assert (written == owned).all(), "every owned output mode must have exactly one head piece"
     # back to the reference layout
     res = out.T.reshape((J + 1,) + dim * (n1,))
     return np.roll(res, dim * (-L,), axis=tuple(range(1, dim + 1)))
 
 
-@pytest.mark.parametrize("name,over,dense", [("ops_golden_L5J5", dict(L=5, J=5), False),
-                                             ("ops_golden_L5J5", dict(L=5, J=5), True),
-                                             ("ops_spiral_L4J4", dict(L=4, J=4, torus="spiral"), False)])
-def test_schedule_replay_matches_oracle(name, over, dense):
+@pytest.mark.parametrize("name,over,mode", [("ops_golden_L5J5", dict(L=5, J=5), 0),
+                                            ("ops_golden_L5J5", dict(L=5, J=5), 1),
+                                            ("ops_golden_L5J5", dict(L=5, J=5), 2),
+                                            ("ops_golden_L7J4", dict(L=7, J=4), 2),
+                                            ("ops_spiral_L4J4", dict(L=4, J=4, torus="spiral"), 0),
+                                            ("ops_spiral_L4J4", dict(L=4, J=4, torus="spiral"), 2)])
+def test_schedule_replay_matches_oracle(name, over, mode):
     g = golden(name)
     c = ro.OracleRG(ro.default_params(**over))
     c.Omega_nu = g["op_Omega_nu"].copy()
-    sched = fetch_schedule(c, dense)
+    sched = fetch_schedule(c, mode)
     assert sched["nw"] * 32 >= c.M
     lanes = sched["lane_out"][sched["lane_out"] >= 0]
-    assert sorted(lanes) == list(range(c.M)), "every output mode owned by exactly one lane"
-    got = replay(c, sched, g["op_y1"], g["op_y2"], g["op_g"], g["op_Omega_nu"], dense)
+    want_lanes = list(range(c.M)) if mode != 2 else list(range((c.M + 1) // 2))   # half space: centred index <= centre
+    assert sorted(lanes) == want_lanes, "every output mode owned by exactly one lane"
+    got = replay(c, sched, g["op_y1"], g["op_y2"], g["op_g"], g["op_Omega_nu"])
     yg = (0.0, g["op_y1"], g["op_y2"], g["op_y3"])
     want = c.liouville(yg, g["op_g"])          # y0 = 0: only the two convolutions
+    if mode == 2:
+        keep = np.zeros(c.M, dtype=bool)
+        keep[:(c.M + 1) // 2] = True
+        keep = np.roll(keep.reshape(c.dim * (2 * c.L + 1,)), c.dim * (-c.L,), axis=tuple(range(c.dim)))
+        got, want = got * keep, want * keep
     assert relmax(got, want) < 1e-13
 
 
 def test_schedule_geometry_config4():
     """The L=J=10 schedule: 14 warps, I^- support of 252 modes, every box in at most two pieces."""
     c = ro.OracleRG(ro.default_params(L=10, J=10))
-    s = fetch_schedule(c, False)
-    assert s["nw"] == 14 and s["ns"] == 252
-    for box in range(s["nw"]):
-        n_pieces = sum(1 for p in s["pieces"] if p[3] != 0 and p[0] == box)
-        assert 1 <= n_pieces <= 2
-    # pieces are balanced to within 10% of the mean cost (cost ~ entries here, jm is mostly J+1)
-    cost = np.zeros(s["nw"])
-    for w in range(s["nw"]):
-        for q in range(2):
-            b, e, mode = s["pieces"][w * 2 + q][1:]
-            if mode:
-                cost[w] += e - b
-    assert cost.max() <= 1.35 * cost.mean()
+    for mode, nb in ((0, 14), (2, 7)):
+        s = fetch_schedule(c, mode)
+        assert s["nw"] == 14 and s["nb"] == nb and s["ns"] == 252
+        useful, issued, cmax, ctot = s["cost"]
+        assert cmax * s["nw"] <= 1.03 * ctot, "per-warp list costs are balanced to 3%"
+        assert useful / issued > 0.6
+    # the half-space schedule does half the work of the full one
+    full, half = fetch_schedule(c, 0)["cost"], fetch_schedule(c, 2)["cost"]
+    assert abs(half[0] / full[0] - 0.5) < 0.01
