@@ -74,6 +74,9 @@ typedef struct {
     int64_t rg_maps;   /* RG.rg_map calls (RG.py:207-228) */
     int64_t conv_fma_executed; /* warp-lane FMAs issued by the convolution loops (incl. predicated lanes) */
     int64_t conv_fma_useful;   /* FMAs on structurally non-zero, in-range operand pairs */
+    int64_t clk_conv;          /* SM clocks inside the bracket convolution, summed over Hamiltonians */
+    int64_t clk_epilogue;      /* SM clocks inside the series epilogue (update + norms), summed */
+    int64_t clk_total;         /* SM clocks from ticket to result, summed over Hamiltonians */
     float kernel_ms;           /* device time of the last batched call (CUDA events on the plan's stream) */
     int32_t launches;          /* kernels launched by the last call */
 } rg_stats;

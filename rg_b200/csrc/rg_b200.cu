@@ -75,7 +75,7 @@ __device__ __forceinline__ void store_wrapped(const DevPlan& P, const double* __
 }
 
 template <int J>
-__global__ void __launch_bounds__(512, 1) rg_kernel(const int slot, const __grid_constant__ Tables T, const __grid_constant__ Job job) {
+__global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_kernel(const int slot, const __grid_constant__ Tables T, const __grid_constant__ Job job) {
     Ctx c;
     c.slot = slot;
     c.sidx = job.sched;
@@ -97,7 +97,8 @@ __global__ void __launch_bounds__(512, 1) rg_kernel(const int slot, const __grid
         __syncthreads();
         const int item = *sh_item;
         if (item >= job.n) break;
-        c.n_liou = 0; c.n_lie = 0; c.symm = 0;
+        c.n_liou = 0; c.n_lie = 0; c.symm = 0; c.t_conv = 0; c.t_epi = 0;
+        const long long t_item = clock64();
         c.rng = 0x243F6A8885A308D3ull ^ ((uint64_t)(item + 1) * 0x9E3779B97F4A7C15ull);
         long long n_maps = 0;
         double* f = fa;
@@ -195,6 +196,8 @@ __global__ void __launch_bounds__(512, 1) rg_kernel(const int slot, const __grid
         }
         if (threadIdx.x == 0 && job.n_liou) {
             job.n_liou[item] = c.n_liou; job.n_lie[item] = c.n_lie; job.n_maps[item] = n_maps;
+            job.n_maps[(size_t)job.n + item] = c.t_conv; job.n_maps[2 * (size_t)job.n + item] = c.t_epi;
+            job.n_maps[3 * (size_t)job.n + item] = clock64() - t_item;
         }
     }
 }
@@ -352,6 +355,18 @@ static kern_t pick_kernel(int J) {
     }
 }
 
+// warps per CTA: one lane per output mode -> ceil(M/32) boxes; rounded up to a multiple of 4 so that the four
+// SM sub-partitions carry the same number of warps (14 warps ran 12 % slower than 16: 4+4+3+3), capped at 16
+// (512 threads x 128 registers = the whole register file).
+static int rg_warps_for(int M) {
+    int w = (((M + 31) / 32 + 3) / 4) * 4;
+    if (w < 4) w = 4;
+    if (w > 12) w = 12;   // 384 threads x 168 registers: the convolution loop needs ~150 registers to run spill-free
+    const char* e = getenv("RG_B200_WARPS");
+    if (e && atoi(e) >= 4 && atoi(e) <= 12 && atoi(e) % 4 == 0) w = atoi(e);
+    return w;
+}
+
 static size_t smem_bytes(const rg_plan* p, int s) {
     const rgplan::Geometry& g = p->g;
     size_t b = (size_t)(g.M + 1 + p->hs[s].n_support) * g.rec_units * 16;
@@ -387,15 +402,16 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     p->g.init(prm->dim, prm->L, prm->J);
     const rgplan::Geometry& g = p->g;
     std::vector<uint16_t> mask = masks_from_iminus(g, prm->iminus);
-    const int n_warps = (g.M + 31) / 32;
+    const int n_warps = rg_warps_for(g.M);
     p->hs[0] = rgplan::make_schedule(g, mask, false, false, n_warps);
     p->hs[1] = rgplan::make_schedule(g, mask, true, false, n_warps);
     p->hs[2] = rgplan::make_schedule(g, mask, false, true, n_warps);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, p->device));
     p->sm_count = prop.multiProcessorCount;
-    p->threads = p->hs[0].n_warps * 32;
-    if (p->threads > 512) { delete p; return fail(-5, "(2L+1)^dim > 512 modes: one CTA cannot own a Hamiltonian of this size yet"); }
+    p->threads = n_warps * 32;
+    for (int s = 0; s < 3; ++s)
+        if (p->hs[s].n_warps != n_warps) { delete p; return fail(-5, "too many output modes for one CTA's convolution schedule"); }
     DevPlan& dp = p->dp;
     memset(&dp, 0, sizeof(dp));
     dp.dim = g.dim; dp.L = g.L; dp.J = g.J; dp.JP = g.JP; dp.n1 = g.n1; dp.M = g.M; dp.vecjl = g.vecjl;
@@ -406,6 +422,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     dp.tol_min = prm->tol_min; dp.tol_max = prm->tol_max; dp.max_lie = prm->max_lie; dp.ct = prm->ct;
     dp.min_step = prm->min_step; dp.abs_tol = prm->abs_tol; dp.rel_tol = prm->rel_tol; dp.eigenvalue = prm->eigenvalue;
     dp.max_series = prm->max_series > 0 ? prm->max_series : 100000;
+    dp.debug = getenv("RG_B200_DEBUG") ? atoi(getenv("RG_B200_DEBUG")) : 0;
     // centred tables
     std::vector<double> om0(g.M), normw(g.M);
     std::vector<int> reidx(g.M), c2w(g.M);
@@ -587,9 +604,9 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     const rgplan::Geometry& g = p->g;
     long long* d_cnt = nullptr;
     if (stats) {
-        CU(cudaMalloc(&d_cnt, sizeof(long long) * 3 * (size_t)std::max(job.n, 1)));
+        CU(cudaMalloc(&d_cnt, sizeof(long long) * 6 * (size_t)std::max(job.n, 1)));
         st.tmp.push_back(d_cnt);
-        CU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 3 * (size_t)std::max(job.n, 1), p->stream));
+        CU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 6 * (size_t)std::max(job.n, 1), p->stream));
         job.n_liou = d_cnt; job.n_lie = d_cnt + job.n; job.n_maps = d_cnt + 2 * (size_t)job.n;
     }
     CU(cudaMemsetAsync(p->ticket, 0, sizeof(int), p->stream));
@@ -602,11 +619,15 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev1, p->stream));
     if (stats) {
-        std::vector<long long> h(3 * (size_t)std::max(job.n, 1));
+        std::vector<long long> h(6 * (size_t)std::max(job.n, 1));
         CU(cudaMemcpyAsync(h.data(), d_cnt, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
         memset(stats, 0, sizeof(*stats));
-        for (int i = 0; i < job.n; ++i) { stats->liouville += h[i]; stats->lie_steps += h[job.n + i]; stats->rg_maps += h[2 * (size_t)job.n + i]; }
+        for (int i = 0; i < job.n; ++i) {
+            stats->liouville += h[i]; stats->lie_steps += h[job.n + i]; stats->rg_maps += h[2 * (size_t)job.n + i];
+            stats->clk_conv += h[3 * (size_t)job.n + i]; stats->clk_epilogue += h[4 * (size_t)job.n + i];
+            stats->clk_total += h[5 * (size_t)job.n + i];
+        }
         // fused modes run the half-space schedule for the series (the 1-norm estimator of expm_multiply runs
         // the full one; its share is accounted at the half-space cost, i.e. under-counted)
         const int sa = (s == 0) ? 2 : s;
@@ -849,7 +870,8 @@ extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_
     if (dim < 1 || dim > 3 || J < 1 || J > 15 || L < 1) return fail(-2, "bad geometry");
     rgplan::Geometry g; g.init(dim, L, J);
     std::vector<uint16_t> mask = masks_from_iminus(g, iminus_wrapped);
-    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, (g.M + 31) / 32);
+    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, rg_warps_for(g.M));
+    if (s.n_warps < 0) return fail(-5, "too many output modes for one CTA's convolution schedule");
     *n_warps = s.n_warps; *n_boxes = s.n_boxes; *n_entries = (int)s.entries.size() / 2; *n_support = s.n_support;
     if (cost) { cost[0] = s.fma_useful; cost[1] = s.fma_executed; cost[2] = s.cost_max; cost[3] = s.cost_total; }
     *lane_out = (int32_t*)malloc(sizeof(int32_t) * s.lane_out.size());

@@ -30,6 +30,8 @@ struct DevPlan {
     int max_lie, ct;
     double min_step, abs_tol, rel_tol, eigenvalue;
     int max_series;
+    int debug;   // RG_B200_DEBUG experiments (0 in production): bit0 gather always hits the zero record,
+                 // bit1 every entry broadcasts y record 0
     const double* omega0_nu;  // [M] centred
     const uint16_t* mask;     // [M] I^- bits per Taylor level
     const int* reidx;         // [M] centred -> centred source, -1 masked
@@ -59,6 +61,7 @@ struct Ctx {
     const double* Omega_nu;  // current Omega.nu, centred, global
     long long n_liou, n_lie;
     uint64_t rng;  // state of the 1-norm estimator's +-1 columns (seeded per Hamiltonian)
+    long long t_conv, t_epi;  // SM clocks spent in conv_all / series_epilogue (thread 0's view; profiling aid)
 };
 
 struct Smem {
@@ -110,57 +113,91 @@ __device__ __forceinline__ double2 block_reduce2(double* red, int type, double a
 
 // ------------------------------------------------------------------------------------------------
 // Taylor product of one (nu1, nu2) pair: acc[j] += sum_{j1+j2=j} dAy[j1]*Omg[j2] - Omy[j1]*dAg[j2]
-// record layout (doubles): [0..J-1] d-type, [OFF2..OFF2+J] Omega-type, y1[J] (caller-supplied y only) at IDXJ
+// record layout (doubles): [0..J-1] d-type, [OFF2..OFF2+J] Omega-type, y1[J] (caller-supplied y only) at IDXJ.
+//
+// Everything the inner loop reads from shared memory is in flight long before it is consumed:
+//   * the two halves of the gathered record G[nu-nu1] live in separate registers; the d-half is loaded
+//     while the Omega-half is consumed (first convolution) and the next entry's Omega-half while the
+//     d-half is consumed (second convolution);
+//   * the broadcast y values go through a rolling window of YW double2 registers that runs across entry
+//     boundaries: pair k+YW is requested the moment pair k is taken out of the window.
 template <int J>
-__device__ __forceinline__ void taylor(double (&acc)[J + 1], const double2* __restrict__ gp,
-                                       const double2* __restrict__ yp, int jm) {
-    constexpr int JP = J + 1, OFF2 = J + (J & 1), TOT = OFF2 + JP, NU2 = (TOT + 1) / 2;
-    constexpr int IDXJ = (J & 1) ? J : OFF2 + JP;
-    double g[2 * NU2];
+struct RecGeom {
+    static constexpr int JP = J + 1, OFF2 = J + (J & 1), TOT = OFF2 + JP, NU2 = (TOT + 1) / 2;
+    static constexpr int ND2 = OFF2 / 2;      // double2 units of the d-type half
+    static constexpr int NO2 = NU2 - ND2;     // double2 units of the Omega-type half
+    static constexpr int IDXJ = (J & 1) ? J : OFF2 + JP;
+    static constexpr int NP1 = (J + 1) / 2;   // y pairs of conv(dA y, Omega g): y1[0..J-1]
+    static constexpr int NP2 = J / 2 + 1;     // y pairs of conv(Omega y, dA g): y2[0..J]
+    static constexpr int NP = NP1 + NP2;
+    static constexpr int YW = 4;              // prefetch window (pairs)
+    static constexpr int NPAD = ((NP + YW - 1) / YW) * YW;   // the window must line up across entries
+    // double2 unit of the k-th y pair in consumption order (indices >= NP are padding: re-read the last pair)
+    __host__ __device__ static constexpr int unit(int k) { return k < NP1 ? k : (k < NP ? ND2 + (k - NP1) : ND2 + NP2 - 1); }
+};
+
+template <int J>
+__device__ __forceinline__ void load_omega_half(double (&gO)[2 * RecGeom<J>::NO2], const double2* __restrict__ gp) {
 #pragma unroll
-    for (int u = 0; u < NU2; ++u) { double2 t = gp[u]; g[2 * u] = t.x; g[2 * u + 1] = t.y; }
-    // conv(dA y, Omega g): y1[j1] = yd[j1], needs j1+1 < jm ; B1[j2] = g[OFF2+j2]
+    for (int u = 0; u < RecGeom<J>::NO2; ++u) { const double2 t = gp[RecGeom<J>::ND2 + u]; gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
+}
+template <int J>
+__device__ __forceinline__ void load_d_half(double (&gD)[2 * RecGeom<J>::ND2], const double2* __restrict__ gp) {
 #pragma unroll
-    for (int u = 0; 2 * u < J; ++u) {
-        if (2 * u + 1 < jm) {
-            double2 t = yp[u];
-            {
-                const int j1 = 2 * u;
+    for (int u = 0; u < RecGeom<J>::ND2; ++u) { const double2 t = gp[u]; gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
+}
+
+// One list entry.  FULL: every Taylor level of y present (jm == J+1) -> branch-free.
+// yq: window holding pairs 0..YW-1 of this entry on entry, pairs 0..YW-1 of the next entry on exit.
+template <int J, bool FULL>
+__device__ __forceinline__ void taylor_entry(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
+                                             const double (&gD)[2 * RecGeom<J>::ND2], double2 (&yq)[RecGeom<J>::YW],
+                                             const double2* __restrict__ yp, const double2* __restrict__ yp_n,
+                                             const double2* __restrict__ gp_n, int jm) {
+    typedef RecGeom<J> R;
+    constexpr int JP = J + 1;
 #pragma unroll
-                for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, g[OFF2 + j2], acc[j1 + j2]);
+    for (int k = 0; k < R::NPAD; ++k) {
+        const double2 t = yq[k % R::YW];
+        if (k + R::YW < R::NPAD) yq[k % R::YW] = yp[R::unit(k + R::YW)];
+        else yq[k % R::YW] = yp_n[R::unit(k + R::YW - R::NPAD)];
+        if (k >= R::NP) continue;   // padding pair
+        if (k < R::NP1) {
+            // conv(dA y, Omega g): y1[j1] = (j1+1) y[j1+1] is non-zero iff j1+1 < jm ; B1[j2] = gO[j2]
+            const int j1 = 2 * k;
+            if (FULL || j1 + 1 < jm) {
+#pragma unroll
+                for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, gO[j2], acc[j1 + j2]);
             }
-            if (2 * u + 1 < J && 2 * u + 2 < jm) {
-                const int j1 = 2 * u + 1;
+            if (j1 + 1 < J && (FULL || j1 + 2 < jm)) {
 #pragma unroll
-                for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.y, g[OFF2 + j2], acc[j1 + j2]);
+                for (int j2 = 0; j2 <= J - j1 - 1; ++j2) acc[j1 + 1 + j2] = fma(t.y, gO[j2], acc[j1 + 1 + j2]);
             }
-        }
-    }
-    if (JP < jm) {  // caller-supplied y with y1[J] != 0 (never on the fused path)
-        double a = reinterpret_cast<const double*>(yp)[IDXJ];
-        acc[J] = fma(a, g[OFF2], acc[J]);
-    }
-    // conv(Omega y, dA g): y2[j1] = yd[OFF2+j1], needs j1 < jm ; B2[j2] = g[j2], j2 < J
-#pragma unroll
-    for (int u = 0; 2 * u <= J; ++u) {
-        if (2 * u < jm) {
-            double2 t = yp[OFF2 / 2 + u];
-            {
-                const int j1 = 2 * u;
-#pragma unroll
-                for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, g[j2], acc[j1 + j2]);
+            if (k == R::NP1 - 1) {
+                if (!FULL && JP < jm) {  // caller-supplied y with y1[J] != 0 (never on the fused path)
+                    const double a = reinterpret_cast<const double*>(yp)[R::IDXJ];
+                    acc[J] = fma(a, gO[0], acc[J]);
+                }
+                load_omega_half<J>(gO, gp_n);   // next entry's Omega-half lands while the d-half is consumed
             }
-            if (2 * u + 1 <= J && 2 * u + 1 < jm) {
-                const int j1 = 2 * u + 1;
+        } else {
+            // conv(Omega y, dA g): y2[j1] non-zero iff j1 < jm ; B2[j2] = gD[j2], j2 < J ; subtracted
+            const int j1 = 2 * (k - R::NP1);
+            if (FULL || j1 < jm) {
 #pragma unroll
-                for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.y, g[j2], acc[j1 + j2]);
+                for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, gD[j2], acc[j1 + j2]);
+            }
+            if (j1 + 1 <= J && (FULL || j1 + 1 < jm)) {
+#pragma unroll
+                for (int j2 = 0; j2 < J && j1 + 1 + j2 <= J; ++j2) acc[j1 + 1 + j2] = fma(-t.y, gD[j2], acc[j1 + 1 + j2]);
             }
         }
     }
 }
 
 template <int J>
-__device__ __forceinline__ void conv_piece(const Ctx& c, int box_warp, int e_begin, int e_end, double (&acc)[J + 1]) {
+__device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, int e_end, double (&acc)[J + 1]) {
+    typedef RecGeom<J> R;
     const DevPlan& P = RG_PLAN(c);
     const Sched& S = RG_SCHED(c);
     const Smem sm = smem_view(P, S);
@@ -168,26 +205,49 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box_warp, int e_beg
     const double2* const Y = sm.Y;
     const uint2* const entries = S.entries;
     const int lane = threadIdx.x & 31;
-    const uint32_t mc = S.lane_coord[box_warp * 32 + lane];
+    const uint32_t mc = S.lane_coord[box * 32 + lane];
     const int L = P.L, s0 = P.stride0, s1 = P.stride1, s2 = P.stride2, Mz = P.M;
     const int v0 = (int)(mc & 0xff) + L, v1 = (int)((mc >> 8) & 0xff) + L, v2 = (int)((mc >> 16) & 0xff) + L;
     const unsigned lim = 2u * (unsigned)L;
     const int RU = P.rec_units;
+    const int dbg = P.debug;
+    double gO[2 * R::NO2], gD[2 * R::ND2];
+    double2 yq[R::YW];
 #pragma unroll
     for (int j = 0; j <= J; ++j) acc[j] = 0.0;
+    // decode entry i of the current chunk: gathered record of this lane, broadcast record of y, Taylor levels
+    auto decode = [&](const uint2& me, int i, const double2*& gp, const double2*& yp, int& jm) {
+        const uint32_t ec = __shfl_sync(0xffffffffu, me.x, i);
+        const uint32_t ei = __shfl_sync(0xffffffffu, me.y, i);
+        jm = (int)(ei & 0xff);
+        const int u0 = v0 - (int)(ec & 0xff), u1 = v1 - (int)((ec >> 8) & 0xff), u2 = v2 - (int)((ec >> 16) & 0xff);
+        const bool ok = ((unsigned)u0 <= lim) & ((unsigned)u1 <= lim) & ((unsigned)u2 <= lim);
+        int gi = ok ? (u0 * s0 + u1 * s1 + u2 * s2) : Mz;
+        int yi = (int)(ei >> 8);
+        if (dbg & 1) gi = Mz;
+        if (dbg & 2) yi = 0;
+        gp = G + gi * RU;
+        yp = Y + yi * RU;
+    };
     for (int base = e_begin; base < e_end; base += 32) {
         uint2 me = make_uint2(0u, 0u);
         if (base + lane < e_end) me = entries[base + lane];
         const int cnt = min(32, e_end - base);
+        const double2 *gp, *yp, *gp_n, *yp_n;
+        int jm, jm_n;
+        decode(me, 0, gp, yp, jm);
+        load_omega_half<J>(gO, gp);
+#pragma unroll
+        for (int k = 0; k < R::YW; ++k) yq[k] = yp[R::unit(k)];
+#pragma unroll 1
         for (int i = 0; i < cnt; ++i) {
-            const uint32_t ec = __shfl_sync(0xffffffffu, me.x, i);
-            const uint32_t ei = __shfl_sync(0xffffffffu, me.y, i);
-            const int jm = (int)(ei & 0xff);
-            const int rec = (int)(ei >> 8);
-            const int u0 = v0 - (int)(ec & 0xff), u1 = v1 - (int)((ec >> 8) & 0xff), u2 = v2 - (int)((ec >> 16) & 0xff);
-            const bool ok = ((unsigned)u0 <= lim) & ((unsigned)u1 <= lim) & ((unsigned)u2 <= lim);
-            const int gi = ok ? (u0 * s0 + u1 * s1 + u2 * s2) : Mz;
-            taylor<J>(acc, G + gi * RU, Y + rec * RU, jm);
+            load_d_half<J>(gD, gp);                       // lands while the first convolution runs
+            // the last entry of a chunk prefetches from its own records (harmless, keeps the loop uniform)
+            gp_n = gp; yp_n = yp; jm_n = jm;
+            if (i + 1 < cnt) decode(me, i + 1, gp_n, yp_n, jm_n);
+            if (jm == J + 1) taylor_entry<J, true>(acc, gO, gD, yq, yp, yp_n, gp_n, jm);
+            else taylor_entry<J, false>(acc, gO, gD, yq, yp, yp_n, gp_n, jm);
+            gp = gp_n; yp = yp_n; jm = jm_n;
         }
     }
 }
@@ -202,6 +262,7 @@ __device__ __noinline__ void conv_all(Ctx& c) {
     const Sched& S = RG_SCHED(c);
     double* const out = smem_view(RG_PLAN(c), S).out;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long t_begin = clock64();
     double acc[JP];
     int4 held = make_int4(-1, 0, 0, 0);
     if (w < S.n_warps) {
@@ -231,6 +292,7 @@ __device__ __noinline__ void conv_all(Ctx& c) {
         __syncthreads();
     }
     c.n_liou++;
+    c.t_conv += clock64() - t_begin;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -285,6 +347,7 @@ __device__ __noinline__ double2 series_epilogue(Ctx& c, double* __restrict__ f, 
     const int nmax = half ? (M + 1) / 2 : M;
     const double* y3 = c.ws + (size_t)WS_Y3 * P.vecjl;
     const Smem sm = smem_view(P, RG_SCHED(c));
+    const long long t_begin = clock64();
     double ps = 0.0, pf = 0.0;
     for (int nu = threadIdx.x; nu < nmax; nu += blockDim.x) {
         double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
@@ -329,7 +392,9 @@ __device__ __noinline__ double2 series_epilogue(Ctx& c, double* __restrict__ f, 
             }
         }
     }
-    return block_reduce2(sm.red, type, ps, pf);
+    const double2 res = block_reduce2(sm.red, type, ps, pf);
+    c.t_epi += clock64() - t_begin;
+    return res;
 }
 
 __device__ __noinline__ void copy_arr(const Ctx& c, double* dst, const double* src) {

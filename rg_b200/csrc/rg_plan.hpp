@@ -172,6 +172,7 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
                 ++k;
             }
             pc.end = (int)s.entries.size() / 2;
+            if (npieces[w] >= MAXP) { s.n_warps = -1; return s; }   // too many boxes for this CTA; reported by the caller
             // heads first, the continuation (if any) last
             if (rank == 0) {
                 int q = npieces[w];
