@@ -147,52 +147,134 @@ __device__ __forceinline__ void load_d_half(double (&gD)[2 * RecGeom<J>::ND2], c
     for (int u = 0; u < RecGeom<J>::ND2; ++u) { const double2 t = gp[u]; gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
 }
 
-// One list entry.  FULL: every Taylor level of y present (jm == J+1) -> branch-free.
+// Per-lane constants of the gather: biased coords of the lane's output mode, its linear index, limits.
+struct LaneGeo {
+    int v0, v1, v2;       // coords + L  (so that v - e, e = biased coord of nu1, is the biased coord of nu - nu1)
+    int lin;              // sum_d v_d * stride_d : centred index of (nu - nu1) = lin - index(nu1)
+    unsigned lim;         // 2L
+    int zero_rec;         // index of the all-zero record (M)
+    uint32_t g_base, y_base;  // shared-memory byte addresses of G and Y
+    int rec_bytes;
+};
+
+// next entry: broadcast the list words, test nu - nu1 against the grid, form the two record addresses
+__device__ __forceinline__ void decode_entry(const LaneGeo& q, const uint2& me, int i, uint32_t& gp, uint32_t& yp, int& jm) {
+    const uint32_t ec = __shfl_sync(0xffffffffu, me.x, i);
+    const uint32_t ei = __shfl_sync(0xffffffffu, me.y, i);
+    jm = (int)(ec >> 24);
+    const unsigned u0 = (unsigned)(q.v0 - (int)(ec & 0xff)), u1 = (unsigned)(q.v1 - (int)((ec >> 8) & 0xff)),
+                   u2 = (unsigned)(q.v2 - (int)((ec >> 16) & 0xff));
+    const bool ok = max(max(u0, u1), u2) <= q.lim;
+    const int gi = ok ? (q.lin - (int)(ei & 0xffff)) : q.zero_rec;
+    gp = q.g_base + (uint32_t)(gi * q.rec_bytes);
+    yp = q.y_base + (uint32_t)((int)(ei >> 16) * q.rec_bytes);
+}
+
+__device__ __forceinline__ double2 lds128(uint32_t addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+
+// One list entry with every Taylor level of y present (jm == J+1): branch-free; the decode of the next entry
+// sits inside the DFMA stream (same basic block) so that its latency chain is hidden.
 // yq: window holding pairs 0..YW-1 of this entry on entry, pairs 0..YW-1 of the next entry on exit.
-template <int J, bool FULL>
-__device__ __forceinline__ void taylor_entry(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
-                                             const double (&gD)[2 * RecGeom<J>::ND2], double2 (&yq)[RecGeom<J>::YW],
-                                             const double2* __restrict__ yp, const double2* __restrict__ yp_n,
-                                             const double2* __restrict__ gp_n, int jm) {
+// gO: Omega-half of this entry's gathered record on entry, of the next entry's on exit.
+template <int J>
+__device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
+                                            double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& me, int i_next,
+                                            bool more, uint32_t& gp, uint32_t& yp, int& jm) {
     typedef RecGeom<J> R;
-    constexpr int JP = J + 1;
+    double gD[2 * R::ND2];
+#pragma unroll
+    for (int u = 0; u < R::ND2; ++u) { const double2 t = lds128(gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
+    uint32_t gp_n = gp, yp_n = yp;
+    int jm_n = jm;
 #pragma unroll
     for (int k = 0; k < R::NPAD; ++k) {
         const double2 t = yq[k % R::YW];
-        if (k + R::YW < R::NPAD) yq[k % R::YW] = yp[R::unit(k + R::YW)];
-        else yq[k % R::YW] = yp_n[R::unit(k + R::YW - R::NPAD)];
+        if (k == 1 && more) decode_entry(q, me, i_next, gp_n, yp_n, jm_n);   // after the first block has issued
+        if (k + R::YW < R::NPAD) yq[k % R::YW] = lds128(yp + 16 * R::unit(k + R::YW));
+        else yq[k % R::YW] = lds128(yp_n + 16 * R::unit(k + R::YW - R::NPAD));
         if (k >= R::NP) continue;   // padding pair
         if (k < R::NP1) {
-            // conv(dA y, Omega g): y1[j1] = (j1+1) y[j1+1] is non-zero iff j1+1 < jm ; B1[j2] = gO[j2]
+            // conv(dA y, Omega g): y1[j1] times B1[j2] = gO[j2]
             const int j1 = 2 * k;
-            if (FULL || j1 + 1 < jm) {
 #pragma unroll
-                for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, gO[j2], acc[j1 + j2]);
-            }
-            if (j1 + 1 < J && (FULL || j1 + 2 < jm)) {
+            for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, gO[j2], acc[j1 + j2]);
+            if (j1 + 1 < J) {
 #pragma unroll
                 for (int j2 = 0; j2 <= J - j1 - 1; ++j2) acc[j1 + 1 + j2] = fma(t.y, gO[j2], acc[j1 + 1 + j2]);
             }
-            if (k == R::NP1 - 1) {
-                if (!FULL && JP < jm) {  // caller-supplied y with y1[J] != 0 (never on the fused path)
-                    const double a = reinterpret_cast<const double*>(yp)[R::IDXJ];
-                    acc[J] = fma(a, gO[0], acc[J]);
-                }
-                load_omega_half<J>(gO, gp_n);   // next entry's Omega-half lands while the d-half is consumed
+            if (k == R::NP1 - 1) {   // next entry's Omega-half lands while the d-half is consumed
+#pragma unroll
+                for (int u = 0; u < R::NO2; ++u) { const double2 g2 = lds128(gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
             }
         } else {
-            // conv(Omega y, dA g): y2[j1] non-zero iff j1 < jm ; B2[j2] = gD[j2], j2 < J ; subtracted
+            // conv(Omega y, dA g): y2[j1] times B2[j2] = gD[j2], j2 < J ; subtracted
             const int j1 = 2 * (k - R::NP1);
-            if (FULL || j1 < jm) {
 #pragma unroll
-                for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, gD[j2], acc[j1 + j2]);
-            }
-            if (j1 + 1 <= J && (FULL || j1 + 1 < jm)) {
+            for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, gD[j2], acc[j1 + j2]);
+            if (j1 + 1 <= J) {
 #pragma unroll
                 for (int j2 = 0; j2 < J && j1 + 1 + j2 <= J; ++j2) acc[j1 + 1 + j2] = fma(-t.y, gD[j2], acc[j1 + 1 + j2]);
             }
         }
     }
+    gp = gp_n; yp = yp_n; jm = jm_n;
+}
+
+// One list entry with only the first jm Taylor levels of y present (or, jm = J+2, a caller-supplied generator):
+// blocks run in ascending j1 and stop at the first absent level; y values are read on demand.  Keeps the
+// hand-over protocol of taylor_full (window and gO hold the next entry's data on exit).
+template <int J>
+__device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
+                                               double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& me, int i_next,
+                                               bool more, uint32_t& gp, uint32_t& yp, int& jm) {
+    typedef RecGeom<J> R;
+    constexpr int JP = J + 1;
+    double gD[2 * R::ND2];
+#pragma unroll
+    for (int u = 0; u < R::ND2; ++u) { const double2 t = lds128(gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
+    uint32_t gp_n = gp, yp_n = yp;
+    int jm_n = jm;
+    if (more) decode_entry(q, me, i_next, gp_n, yp_n, jm_n);
+    // conv(dA y, Omega g): y1[j1] = (j1+1) y[j1+1] is non-zero iff j1+1 < jm
+#pragma unroll
+    for (int k = 0; k < R::NP1; ++k) {
+        const int j1 = 2 * k;
+        if (!(j1 + 1 < jm)) break;
+        const double2 t = (k < R::YW) ? yq[k] : lds128(yp + 16 * R::unit(k));
+#pragma unroll
+        for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, gO[j2], acc[j1 + j2]);
+        if (j1 + 1 < J && j1 + 2 < jm) {
+#pragma unroll
+            for (int j2 = 0; j2 <= J - j1 - 1; ++j2) acc[j1 + 1 + j2] = fma(t.y, gO[j2], acc[j1 + 1 + j2]);
+        }
+    }
+    if (JP < jm) {  // caller-supplied y with y1[J] != 0 (never on the fused path)
+        double a;
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(yp + 8 * R::IDXJ));
+        acc[J] = fma(a, gO[0], acc[J]);
+    }
+#pragma unroll
+    for (int u = 0; u < R::NO2; ++u) { const double2 g2 = lds128(gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
+    // conv(Omega y, dA g): y2[j1] non-zero iff j1 < jm ; subtracted
+#pragma unroll
+    for (int k = 0; k < R::NP2; ++k) {
+        const int j1 = 2 * k;
+        if (!(j1 < jm)) break;
+        const double2 t = (R::NP1 + k < R::YW) ? yq[R::NP1 + k] : lds128(yp + 16 * R::unit(R::NP1 + k));
+#pragma unroll
+        for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, gD[j2], acc[j1 + j2]);
+        if (j1 + 1 <= J && j1 + 1 < jm) {
+#pragma unroll
+            for (int j2 = 0; j2 < J && j1 + 1 + j2 <= J; ++j2) acc[j1 + 1 + j2] = fma(-t.y, gD[j2], acc[j1 + 1 + j2]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < R::YW; ++k) yq[k] = lds128(yp_n + 16 * R::unit(k));
+    gp = gp_n; yp = yp_n; jm = jm_n;
 }
 
 template <int J>
@@ -201,53 +283,38 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     const DevPlan& P = RG_PLAN(c);
     const Sched& S = RG_SCHED(c);
     const Smem sm = smem_view(P, S);
-    const double2* const G = sm.G;
-    const double2* const Y = sm.Y;
     const uint2* const entries = S.entries;
     const int lane = threadIdx.x & 31;
     const uint32_t mc = S.lane_coord[box * 32 + lane];
-    const int L = P.L, s0 = P.stride0, s1 = P.stride1, s2 = P.stride2, Mz = P.M;
-    const int v0 = (int)(mc & 0xff) + L, v1 = (int)((mc >> 8) & 0xff) + L, v2 = (int)((mc >> 16) & 0xff) + L;
-    const unsigned lim = 2u * (unsigned)L;
-    const int RU = P.rec_units;
-    const int dbg = P.debug;
-    double gO[2 * R::NO2], gD[2 * R::ND2];
+    LaneGeo q;
+    q.v0 = (int)(mc & 0xff) + P.L; q.v1 = (int)((mc >> 8) & 0xff) + P.L; q.v2 = (int)((mc >> 16) & 0xff) + P.L;
+    q.lin = q.v0 * P.stride0 + q.v1 * P.stride1 + q.v2 * P.stride2;
+    q.lim = 2u * (unsigned)P.L;
+    q.zero_rec = P.M;
+    q.g_base = (uint32_t)__cvta_generic_to_shared(sm.G);
+    q.y_base = (uint32_t)__cvta_generic_to_shared(sm.Y);
+    q.rec_bytes = P.rec_units * 16;
+    double gO[2 * R::NO2];
     double2 yq[R::YW];
 #pragma unroll
     for (int j = 0; j <= J; ++j) acc[j] = 0.0;
-    // decode entry i of the current chunk: gathered record of this lane, broadcast record of y, Taylor levels
-    auto decode = [&](const uint2& me, int i, const double2*& gp, const double2*& yp, int& jm) {
-        const uint32_t ec = __shfl_sync(0xffffffffu, me.x, i);
-        const uint32_t ei = __shfl_sync(0xffffffffu, me.y, i);
-        jm = (int)(ei & 0xff);
-        const int u0 = v0 - (int)(ec & 0xff), u1 = v1 - (int)((ec >> 8) & 0xff), u2 = v2 - (int)((ec >> 16) & 0xff);
-        const bool ok = ((unsigned)u0 <= lim) & ((unsigned)u1 <= lim) & ((unsigned)u2 <= lim);
-        int gi = ok ? (u0 * s0 + u1 * s1 + u2 * s2) : Mz;
-        int yi = (int)(ei >> 8);
-        if (dbg & 1) gi = Mz;
-        if (dbg & 2) yi = 0;
-        gp = G + gi * RU;
-        yp = Y + yi * RU;
-    };
     for (int base = e_begin; base < e_end; base += 32) {
         uint2 me = make_uint2(0u, 0u);
         if (base + lane < e_end) me = entries[base + lane];
         const int cnt = min(32, e_end - base);
-        const double2 *gp, *yp, *gp_n, *yp_n;
-        int jm, jm_n;
-        decode(me, 0, gp, yp, jm);
-        load_omega_half<J>(gO, gp);
+        uint32_t gp, yp;
+        int jm;
+        decode_entry(q, me, 0, gp, yp, jm);
 #pragma unroll
-        for (int k = 0; k < R::YW; ++k) yq[k] = yp[R::unit(k)];
+        for (int u = 0; u < R::NO2; ++u) { const double2 t = lds128(gp + 16 * (R::ND2 + u)); gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
+#pragma unroll
+        for (int k = 0; k < R::YW; ++k) yq[k] = lds128(yp + 16 * R::unit(k));
 #pragma unroll 1
         for (int i = 0; i < cnt; ++i) {
-            load_d_half<J>(gD, gp);                       // lands while the first convolution runs
             // the last entry of a chunk prefetches from its own records (harmless, keeps the loop uniform)
-            gp_n = gp; yp_n = yp; jm_n = jm;
-            if (i + 1 < cnt) decode(me, i + 1, gp_n, yp_n, jm_n);
-            if (jm == J + 1) taylor_entry<J, true>(acc, gO, gD, yq, yp, yp_n, gp_n, jm);
-            else taylor_entry<J, false>(acc, gO, gD, yq, yp, yp_n, gp_n, jm);
-            gp = gp_n; yp = yp_n; jm = jm_n;
+            const bool more = (i + 1 < cnt);
+            if (jm == J + 1) taylor_full<J>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            else taylor_partial<J>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
         }
     }
 }

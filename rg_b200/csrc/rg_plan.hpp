@@ -74,7 +74,7 @@ struct Schedule {
     std::vector<int32_t> lane_out;     // [NB*32] centred mode index or -1
     std::vector<uint32_t> lane_coord;  // [NB*32] packed biased coords (0xFFFFFFFF idle)
     std::vector<Piece> pieces;         // [NW*MAXP], box = -1 for unused slots; heads first, continuation last
-    std::vector<uint32_t> entries;     // [n*2]: {packed biased coords of nu1, (rec<<8)|jm}
+    std::vector<uint32_t> entries;     // [n*2]: {biased coords of nu1 (8 bits each) | jm<<24, centred index | rec<<16}
     std::vector<int32_t> supp_rec;     // [M] record index of centred nu1, -1 if not in support
     std::vector<uint8_t> jm;           // [M] 1 + highest I^- level (0 = not in support)
     int64_t fma_useful = 0;            // per liouville, in-range & structurally non-zero
@@ -146,6 +146,9 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
             }
         }
     }
+    // entries with every Taylor level present first: the branch-free path then runs in long stretches
+    for (int b = 0; b < NB; ++b)
+        std::stable_sort(lists[b].begin(), lists[b].end(), [&](int x, int y) { return (s.jm[x] == g.JP) > (s.jm[y] == g.JP); });
     // ---- deal the concatenated lists to the warps in equal-cost segments.  A warp's segment starts with at
     // most one continuation of a box (rank > 0) followed by heads of later boxes (rank 0).
     s.pieces.assign(NW * MAXP, Piece{-1, 0, 0, 0});
@@ -166,8 +169,9 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
                 const int c1 = lists[b][k];
                 if (w < NW - 1 && acc * NW >= total * (int64_t)(w + 1) && (int)s.entries.size() / 2 > pc.begin) break;
                 int v1[4]; g.coords(c1, v1);
-                s.entries.push_back(g.pack(v1));
-                s.entries.push_back(((uint32_t)s.supp_rec[c1] << 8) | s.jm[c1]);
+                // word0: biased coords (validity test) | jm<<24 ; word1: centred linear index | record<<16
+                s.entries.push_back(g.pack(v1) | ((uint32_t)s.jm[c1] << 24));
+                s.entries.push_back((uint32_t)c1 | ((uint32_t)s.supp_rec[c1] << 16));
                 acc += tcost(c1); wcost[w] += tcost(c1);
                 ++k;
             }

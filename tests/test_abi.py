@@ -141,9 +141,9 @@ def replay(c, sched, y1, y2, g, Omega_nu):
             acc = np.zeros((32, J + 1))
             for ent in sched["entries"][b:e]:
                 ec = [(int(ent[0]) >> (8 * d)) & 0xff for d in range(dim)]
-                jm, rec = int(ent[1]) & 0xff, int(ent[1]) >> 8
+                jm, rec = int(ent[0]) >> 24, int(ent[1]) >> 16
                 nu1 = nu_of_rec[rec]
-                assert list(coords[nu1]) == ec
+                assert list(coords[nu1]) == ec and (int(ent[1]) & 0xffff) == nu1
                 for l, nu in enumerate(lanes):
                     if nu < 0:
                         continue
