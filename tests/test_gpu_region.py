@@ -21,10 +21,35 @@ def run_region(c, g):
     return data[:, :, 0], data[:, :, 1], info
 
 
-def check_maps(c, g, allow=0):
+def near_critical(conv):
+    """Grid cells with a neighbour (8-connectivity) on the other side of the critical surface."""
+    ny, nx = conv.shape
+    m = np.zeros_like(conv, dtype=bool)
+    for dy in (-1, 0, 1):
+        for dx in (-1, 0, 1):
+            a = conv[max(0, dy):ny + min(0, dy), max(0, dx):nx + min(0, dx)]
+            b = conv[max(0, -dy):ny + min(0, -dy), max(0, -dx):nx + min(0, -dx)]
+            m[max(0, dy):ny + min(0, dy), max(0, dx):nx + min(0, dx)] |= (a != b)
+    return m
+
+
+def check_maps(c, g, near_critical_oracle=None):
+    """Bit-exact (flag, count, error) maps.  With `near_critical_oracle` (an OracleRG), grid cells adjacent to
+    the critical surface may differ from the reference golden -- there the reference's own integer result
+    depends on the rounding noise of its FFT convolution -- provided the GPU agrees with the direct-
+    convolution oracle; they are reported separately (BASELINE.json north_star)."""
     conv, count, err = run_region(c, g)
     bad = (conv != g["conv"]) | (count != g["count"]) | (err != g["error"])
-    assert bad.sum() <= allow, ("mismatching points", np.argwhere(bad).tolist(), count[bad].tolist(), g["count"][bad].tolist())
+    if near_critical_oracle is not None and bad.any():
+        assert (bad & ~near_critical(g["conv"])).sum() == 0, ("mismatch away from the critical surface", np.argwhere(bad).tolist())
+        pts = [(g["xs"][ix], g["ys"][iy]) for iy, ix in np.argwhere(bad)]
+        oc, on, oe, _ = near_critical_oracle.points(pts)
+        got = [(int(conv[iy, ix]), int(count[iy, ix]), int(err[iy, ix])) for iy, ix in np.argwhere(bad)]
+        assert got == [(int(a), int(b), int(e)) for a, b, e in zip(oc, on, oe)], ("GPU differs from the oracle", got)
+        print("near-critical points reported separately:", np.argwhere(bad).tolist(), "gpu/oracle", got,
+              "reference", g["count"][bad].tolist())
+    else:
+        assert bad.sum() == 0, ("mismatching points", np.argwhere(bad).tolist(), count[bad].tolist(), g["count"][bad].tolist())
     return c.last_stats
 
 
@@ -65,9 +90,10 @@ def test_region_L10J10_subsample(ct):
 
 def test_region_L10J10_heavy_grid():
     """Secondary, heavier grid of SURVEY 8(d): 12x12 on [0,0.06]x[0,0.08] at L=J=10 (richer boundary)."""
+    import rg_oracle as ro
     g = golden("region_L10J10_12x12_expm_onestep")
     c = make(10, 10, "expm_onestep")
-    check_maps(c, g)
+    check_maps(c, g, near_critical_oracle=ro.OracleRG(ro.default_params(L=10, J=10, CT="expm_onestep")))
     c.close()
 
 
