@@ -42,6 +42,7 @@ extern "C" {
 
 /* internal safety codes written to err[] where the reference would spin forever (quirk Q6) */
 #define RG_ERR_TABLE_EXHAUSTED (-99) /* converge needed more rg_map iterates than the tables hold */
+#define RG_ERR_WORK_BUDGET (-98)     /* a Hamiltonian exceeded max_liouville liouville evaluations */
 #define RG_ERR_SERIES_CAP 1          /* Lie series hit the hard cap: reported like the TolMax abort */
 
 typedef struct rg_plan rg_plan;     /* one per (device, parameter set): RG.__init__ RG.py:51-100 */
@@ -65,6 +66,7 @@ typedef struct {
     int32_t n_theta;
     int32_t device;          /* CUDA device ordinal */
     int32_t max_series;      /* hard cap on Lie-series length (0 = default 100000); the reference has none */
+    int64_t max_liouville;   /* work budget per Hamiltonian in liouville evaluations (0 = default 2 000 000) */
 } rg_params;
 
 /* per-point work counters (also the roofline numerator: liouville evaluations actually executed) */
@@ -101,6 +103,11 @@ int rg_tables_destroy(rg_tables* t);
    conv/count/err [n] int32: int(converge(h)), h.count, h.error.  stats may be NULL. */
 int rg_region(rg_plan* plan, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
               int32_t* conv, int32_t* count, int32_t* err, rg_stats* stats);
+
+/* rg_region that also returns the number of liouville evaluations each point needed (int64 [n], may be
+   NULL): the work measure used by rg_modules.region_maps to order points heaviest-first. */
+int rg_region_work(rg_plan* plan, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
+                   int32_t* conv, int32_t* count, int32_t* err, int64_t* liouville_per_point, rg_stats* stats);
 
 /* RG.converge batched (RG.py:278-290).  f [n][vecjl]; k0[n] = iterate index of each input's Omega in
    `tab` (may be NULL = all 0); err_io[n] carries h.error in and out (untouched on the converged branch). */

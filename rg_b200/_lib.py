@@ -25,7 +25,8 @@ class RGParams(ctypes.Structure):
                 ("min_step", ctypes.c_double), ("abs_tol", ctypes.c_double), ("rel_tol", ctypes.c_double),
                 ("eigenvalue", ctypes.c_double),
                 ("omega0_nu", vp), ("iminus", vp), ("reidx", vp), ("theta", vp),
-                ("n_theta", ctypes.c_int32), ("device", ctypes.c_int32), ("max_series", ctypes.c_int32)]
+                ("n_theta", ctypes.c_int32), ("device", ctypes.c_int32), ("max_series", ctypes.c_int32),
+                ("max_liouville", ctypes.c_int64)]
 
 
 class RGStats(ctypes.Structure):
@@ -47,6 +48,7 @@ SIGNATURES = {
     "rg_tables_create": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, ctypes.POINTER(vp)]),
     "rg_tables_destroy": (ctypes.c_int, [vp]),
     "rg_region": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, ctypes.POINTER(RGStats)]),
+    "rg_region_work": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_converge": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, vp, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_map": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_expm": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp, vp, ctypes.c_double, vp, vp,

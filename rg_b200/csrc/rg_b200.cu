@@ -58,6 +58,7 @@ struct Job {
     double* f_out; double* y0_out; double* y1_out; double* y2_out; double* y3_out;
     long long* n_liou; long long* n_lie; long long* n_maps;
     int* m_out; int* s_out; double* norm1_out;   // mode 6
+    long long* liou_out;                          // optional per-item liouville count
     double* ws_base;
 };
 
@@ -122,17 +123,19 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
             double2 nn = sym_and_norms(c, f, false);
             double ni = nn.y;
             int k = 0, err = 0;
-            bool overflow = false;
+            bool overflow = false, budget = false;
             while (P.tol_max > ni && ni > P.tol_min) {
                 if (k0 + k >= T.n_tab) { overflow = true; break; }
+                if (c.n_liou > P.max_liouville) { budget = true; break; }
                 f = rg_map_dev<J>(c, f, T, k0 + k, err, ni);
                 ++k; ++n_maps;
             }
             if (threadIdx.x == 0) {
-                const bool cv = ni < P.tol_min;
-                job.conv[item] = (cv && !overflow) ? 1 : 0;
-                job.count[item] = (cv && !overflow) ? -k : k;
-                if (overflow) job.err[item] = RG_ERR_TABLE_EXHAUSTED;
+                const bool cv = (ni < P.tol_min) && !overflow && !budget;
+                job.conv[item] = cv ? 1 : 0;
+                job.count[item] = cv ? -k : k;
+                if (budget) job.err[item] = RG_ERR_WORK_BUDGET;
+                else if (overflow) job.err[item] = RG_ERR_TABLE_EXHAUSTED;
                 else if (!cv) job.err[item] = err;
                 else if (job.mode == 0) job.err[item] = 0;
             }
@@ -194,6 +197,7 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
             store_wrapped(P, c.ws + (size_t)WS_Y3 * P.vecjl, job.y3_out + (size_t)item * P.vecjl);
             if (threadIdx.x == 0) job.y0_out[item] = a;
         }
+        if (threadIdx.x == 0 && job.liou_out) job.liou_out[item] = c.n_liou;
         if (threadIdx.x == 0 && job.n_liou) {
             job.n_liou[item] = c.n_liou; job.n_lie[item] = c.n_lie; job.n_maps[item] = n_maps;
             job.n_maps[(size_t)job.n + item] = c.t_conv; job.n_maps[2 * (size_t)job.n + item] = c.t_epi;
@@ -422,6 +426,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     dp.tol_min = prm->tol_min; dp.tol_max = prm->tol_max; dp.max_lie = prm->max_lie; dp.ct = prm->ct;
     dp.min_step = prm->min_step; dp.abs_tol = prm->abs_tol; dp.rel_tol = prm->rel_tol; dp.eigenvalue = prm->eigenvalue;
     dp.max_series = prm->max_series > 0 ? prm->max_series : 100000;
+    dp.max_liouville = prm->max_liouville > 0 ? prm->max_liouville : 2000000LL;
     dp.debug = getenv("RG_B200_DEBUG") ? atoi(getenv("RG_B200_DEBUG")) : 0;
     // centred tables
     std::vector<double> om0(g.M), normw(g.M);
@@ -642,8 +647,15 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
 
 static Tables null_tables() { Tables t; t.n_tab = 0; t.nrm = nullptr; t.Omega_nu = nullptr; return t; }
 
+static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, Stage& st);
+
 extern "C" int rg_region(rg_plan* p, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
                          int32_t* conv, int32_t* count, int32_t* err, rg_stats* stats) {
+    return rg_region_work(p, tab, n, amps, K_flat, nK, conv, count, err, nullptr, stats);
+}
+
+extern "C" int rg_region_work(rg_plan* p, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
+                              int32_t* conv, int32_t* count, int32_t* err, int64_t* liouville_per_point, rg_stats* stats) {
     if (!p || !tab || n < 0 || !amps || !K_flat || nK < 1 || !conv || !count || !err) return fail(-1, "bad argument");
     if (p->dp.ct == RG_CT_MULTIPLY && !RG_HAVE_MULTIPLY) return fail(-7, "expm_multiply not available in this build");
     CU(cudaSetDevice(p->device));
@@ -664,6 +676,7 @@ extern "C" int rg_region(rg_plan* p, const rg_tables* tab, int32_t n, const doub
     if ((rc = st.outp(conv, sizeof(int) * (size_t)n, &o))) return rc; job.conv = (int*)o;
     if ((rc = st.outp(count, sizeof(int) * (size_t)n, &o))) return rc; job.count = (int*)o;
     if ((rc = st.outp(err, sizeof(int) * (size_t)n, &o))) return rc; job.err = (int*)o;
+    if (liouville_per_point) { if ((rc = st.outp(liouville_per_point, sizeof(long long) * (size_t)n, &o))) return rc; job.liou_out = (long long*)o; }
     if ((rc = launch_job(p, tab->t, job, stats, st))) return rc;
     return st.finish();
 }

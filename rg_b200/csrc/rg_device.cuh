@@ -30,6 +30,7 @@ struct DevPlan {
     int max_lie, ct;
     double min_step, abs_tol, rel_tol, eigenvalue;
     int max_series;
+    long long max_liouville;   // work budget per Hamiltonian (the reference has none, quirk Q6)
     int debug;   // RG_B200_DEBUG experiments (0 in production): bit0 gather always hits the zero record,
                  // bit1 every entry broadcasts y record 0
     const double* omega0_nu;  // [M] centred
@@ -491,7 +492,7 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
         if (c1 + c2 < tol * r.y) break;
         else if (c1 + c2 > P.tol_max) { err = 1; break; }
         c1 = c2;
-        if (m >= P.max_series) { err = 1; break; }  // safety: the reference would spin (quirk Q6)
+        if (m >= P.max_series || c.n_liou > P.max_liouville) { err = 1; break; }  // safety: the reference would spin (quirk Q6)
     }
     c.sidx = sidx_saved;
     return err;
@@ -651,7 +652,7 @@ __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, i
     f = dst;
     int err = 0, kl = 0;
     double2 nn = sym_and_norms(c, f, false);
-    while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie) {
+    while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie && c.n_liou <= P.max_liouville) {
         const double a = generate_y(c, f);
         __syncthreads();
         if (P.ct == 0) err = expm_onestep<J>(c, f, a, 1.0);

@@ -244,7 +244,7 @@ __device__ __noinline__ int expm_multiply(Ctx& c, double* f, double a_unscaled) 
     int err = 0;
     // a non-finite or absurd scale would never terminate in the reference either (range(scale)); cap it
     const long long reps = (scale < 1e9) ? (long long)scale : 1000000000LL;
-    for (long long r = 0; r < reps; ++r) {
+    for (long long r = 0; r < reps && c.n_liou <= RG_PLAN(c).max_liouville; ++r) {
         const int e = expm_series<J>(c, f, a_unscaled, 1.0, scale, true, m_star);
         if (e) err = 1;
         __syncthreads();

@@ -215,6 +215,7 @@ class RG:
             prm.n_theta = len(self._theta)
             prm.device = self._device_index()
             prm.max_series = 0
+            prm.max_liouville = int(os.environ.get("RG_B200_MAX_LIOUVILLE", "0"))
             h = ctypes.c_void_p()
             _lib.check(L.rg_plan_create(ctypes.byref(prm), ctypes.byref(h)))
             self._plans[name] = h
@@ -478,9 +479,10 @@ class RG:
             out.append(int(k[0]) * self._M + int(xp.ravel_multi_index(tuple(xp.mod(k[1:], n1)), self.r_jl[1:])))
         return xp.array(out, dtype=xp.int32)
 
-    def points(self, amps, conv=None, count=None, err=None):
+    def points(self, amps, conv=None, count=None, err=None, work=None):
         """`point` for a batch: amps[B, len(K)] (host ndarray, pinned torch tensor or CUDA tensor).
-        Returns (conv, count, error) int32 arrays (or fills the supplied host/device buffers)."""
+        Returns (conv, count, error) int32 arrays (or fills the supplied host/device buffers).
+        `work`: optional int64[B] buffer receiving the liouville evaluations spent on each point."""
         if isinstance(amps, xp.ndarray):
             amps = _f64(amps)
             n = amps.shape[0]
@@ -492,6 +494,6 @@ class RG:
             conv, count, err = (xp.zeros(n, xp.int32) for _ in range(3))
         nrm, onu, oms, tab = self._tables(self.Omega)
         kf = self.K_flat()
-        _lib.check(_lib.lib().rg_region(self._plan(), tab, n, _ptr(amps), kf.ctypes.data, nK, _ptr(conv), _ptr(count),
-                                        _ptr(err), self._stats()))
+        _lib.check(_lib.lib().rg_region_work(self._plan(), tab, n, _ptr(amps), kf.ctypes.data, nK, _ptr(conv), _ptr(count),
+                                             _ptr(err), _ptr(work), self._stats()))
         return conv, count, err

@@ -1,0 +1,79 @@
+"""Drivers of RG_modules on the GPU: compute_line / compute_surface thresholds agree with the reference
+to RelDist, compute_region writes the reference's .mat schema."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def make(**kw):
+    from rg_b200 import RG, make_param_dict
+    kw.setdefault("SaveData", False)
+    return RG(make_param_dict(**kw))
+
+
+def test_compute_line_L5J5(capsys):
+    """G-D: critical threshold along DirLine, RelDist=1e-8 (BASELINE config 2 at the CPU-checkable size)."""
+    from rg_b200 import compute_line
+    g = golden("line_L5J5")
+    c = make(L=5, J=5, CanonicalTransformation="expm_onestep", RelDist=1e-8, Method="line")
+    hl = compute_line(c)
+    eps = np.array([[2 * h.f[k] for k in c.K] for h in hl])
+    assert np.allclose(eps, g["eps"], rtol=2e-8, atol=0), (eps, g["eps"])
+    assert [h.count for h in hl] == [int(v) for v in g["counts"]]
+    assert [h.error for h in hl] == [int(v) for v in g["errors"]]
+    c.close()
+
+
+def test_compute_surface_L5J5(tmp_path, monkeypatch):
+    """G-E: critical surface eps2(eps1), Nxy=8, RelDist=1e-5 (BASELINE config 3 at the CPU-checkable size)."""
+    from rg_b200 import compute_surface
+    monkeypatch.chdir(tmp_path)
+    g = golden("surface_L5J5_n8")
+    c = make(L=5, J=5, CanonicalTransformation="expm_onestep", RelDist=1e-5, Nxy=8, Method="surface", SaveData=True)
+    data = compute_surface(c)
+    assert data.shape == (2, 8)
+    assert np.allclose(data[0], g["data"][0], rtol=0, atol=1e-15)
+    assert np.allclose(data[1], g["data"][1], rtol=2e-5, atol=0), (data[1], g["data"][1])
+    files = [f for f in os.listdir(tmp_path) if f.startswith("RG_surface_") and f.endswith(".mat")]
+    assert len(files) == 1
+    c.close()
+
+
+def test_compute_region_mat_schema(tmp_path, monkeypatch):
+    """compute_region writes RG_region_<timestamp>.mat with data int64 (Nxy,Nxy,2), info (Nxy,Nxy) and every
+    param_dict key except Precision (RG_modules.py:163-173)."""
+    import scipy.io
+    from rg_b200 import compute_region
+    monkeypatch.chdir(tmp_path)
+    g = golden("region_L5J5_8x8_default_expm_onestep")
+    c = make(L=5, J=5, CanonicalTransformation="expm_onestep", Nxy=8, Method="region", SaveData=True)
+    data, info = compute_region(c)
+    assert np.array_equal(data[:, :, 0], g["conv"]) and np.array_equal(data[:, :, 1], g["count"]) and np.array_equal(info, g["error"])
+    files = [f for f in os.listdir(tmp_path) if f.startswith("RG_region_") and f.endswith(".mat")]
+    assert len(files) == 1
+    m = scipy.io.loadmat(os.path.join(tmp_path, files[0]))
+    assert m["data"].shape == (8, 8, 2) and m["info"].shape == (8, 8)
+    for k in c.DictParams:
+        assert (k in m) == (k != "Precision"), k
+    assert "author" in m and "date" in m
+    c.close()
+
+
+def test_compute_iterates_runs(tmp_path, monkeypatch, capsys):
+    """BASELINE config 1 (iterates, L=J=5, expm_adapt): the loop runs and prints (diff, delta, lambda); the
+    reference dies in `eigenvalues` afterwards (quirk Q1), we report it and still save."""
+    from rg_b200 import compute_iterates
+    monkeypatch.chdir(tmp_path)
+    c = make(L=5, J=5, CanonicalTransformation="expm_adapt", RelDist=1e-6, Iterates=2, Method="iterates", SaveData=True)
+    data = compute_iterates(c)
+    assert len(data) == 2 and all(np.isfinite(v) for row in data for v in row)
+    # SURVEY 3.4 probe: (diff, delta, lambda) = (0.274, 4.87, 4.05), (0.554, 3.53, 4.72)
+    assert abs(data[0][0] - 0.274) < 5e-3 and abs(data[0][1] - 4.87) < 5e-2 and abs(data[0][2] - 4.05) < 5e-2
+    assert abs(data[1][0] - 0.554) < 5e-3 and abs(data[1][1] - 3.53) < 5e-2 and abs(data[1][2] - 4.72) < 5e-2
+    assert "eigenvalues unavailable" in capsys.readouterr().out
+    c.close()
