@@ -44,6 +44,9 @@ def parse():
     ap.add_argument("--nxy", type=int, default=GRID["Nxy"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=8, help="side of the strided CPU-baseline subsample")
+    ap.add_argument("--neighbour-queue", action="store_true", help="experimental: heavy points queue their grid neighbours")
+    ap.add_argument("--emulate-world", type=int, default=0,
+                    help="diagnostic: run rank 0's shard of an N-rank job on one GPU (tail / load-balance study)")
     return ap.parse_args()
 
 
@@ -147,7 +150,12 @@ def main_b200(a):
     amps = rg_modules.region_amps(case, x_vec, y_vec)
     n_total = amps.shape[0]
     idx = rg_modules.shard_indices(n_total, rank, world)
+    if a.emulate_world > 1:
+        idx = rg_modules.shard_indices(n_total, 0, a.emulate_world)
+        n_total = len(idx)
     n_loc = len(idx)
+    eff_world = a.emulate_world if a.emulate_world > 1 else world
+    row_len = a.nxy // eff_world if (a.nxy % eff_world == 0 and a.neighbour_queue) else 0
     # host pinned buffers (the public-API path copies them in and out inside the timed region)
     h_amps = torch.from_numpy(amps[idx].copy()).pin_memory()
     h_out = [torch.zeros(n_loc, dtype=torch.int32).pin_memory() for _ in range(3)]
@@ -164,7 +172,7 @@ def main_b200(a):
         flush.fill_(1)                       # L2 flush between iterations
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        case.points(h_amps, *h_out)          # H2D + kernel + D2H through the C ABI
+        case.points(h_amps, *h_out, row_len=row_len)   # H2D + kernel + D2H through the C ABI
         loc = np.stack([t.numpy() for t in h_out], axis=1)
         full = rg_modules.gather_sharded(loc, n_total, rank, world)
         wall = time.perf_counter() - t0

@@ -48,7 +48,8 @@ SIGNATURES = {
     "rg_tables_create": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, ctypes.POINTER(vp)]),
     "rg_tables_destroy": (ctypes.c_int, [vp]),
     "rg_region": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, ctypes.POINTER(RGStats)]),
-    "rg_region_work": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, vp, ctypes.POINTER(RGStats)]),
+    "rg_region_work": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, vp, ctypes.c_int32,
+                                      ctypes.c_int32, ctypes.POINTER(RGStats)]),
     "rg_converge": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, vp, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_map": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_expm": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp, vp, ctypes.c_double, vp, vp,

@@ -59,6 +59,8 @@ struct Job {
     long long* n_liou; long long* n_lie; long long* n_maps;
     int* m_out; int* s_out; double* norm1_out;   // mode 6
     long long* liou_out;                          // optional per-item liouville count
+    // heavy-neighbour scheduling (region grids): a point that turns out heavy queues its grid neighbours
+    int* claimed; int* prio_q; int* q_ctr; int row_len; int hot_threshold; int q_cap;
     double* ws_base;
 };
 
@@ -72,6 +74,44 @@ __device__ __forceinline__ void store_wrapped(const DevPlan& P, const double* __
     for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
         const int j = i / P.M, c = i - j * P.M;
         dst[j * P.M + P.c2w[c]] = src[i];
+    }
+}
+
+// ---- work distribution.  Default: an atomic ticket over the items in array order.  Region grids add a
+// priority queue: cost is spatially coherent (the heavy points hug the critical surface), so a point that
+// has already spent `hot_threshold` liouville evaluations queues its four grid neighbours; idle CTAs drain
+// that queue before the ticket.  Results do not depend on the order in which points are processed.
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+
+__device__ int fetch_item(const Job& job) {
+    if (job.row_len > 0) {
+        for (;;) {
+            const int h = ld_volatile(&job.q_ctr[2]), t = ld_volatile(&job.q_ctr[1]);
+            if (h >= t) break;
+            if (atomicCAS(&job.q_ctr[2], h, h + 1) != h) continue;
+            const int it = ld_volatile(&job.prio_q[h]);
+            if (atomicCAS(&job.claimed[it], 0, 1) == 0) return it;
+        }
+        for (;;) {
+            const int i = atomicAdd(job.ticket, 1);
+            if (i >= job.n) return job.n;
+            if (atomicCAS(&job.claimed[i], 0, 1) == 0) return i;
+        }
+    }
+    return atomicAdd(job.ticket, 1);
+}
+
+__device__ void push_neighbours(const Job& job, int item) {
+    const int rl = job.row_len, col = item % rl;
+    const int nb[4] = {col > 0 ? item - 1 : -1, col + 1 < rl ? item + 1 : -1, item - rl, item + rl};
+    for (int q = 0; q < 4; ++q) {
+        const int it = nb[q];
+        if (it < 0 || it >= job.n || ld_volatile(&job.claimed[it]) != 0) continue;
+        const int slot = atomicAdd(&job.q_ctr[0], 1);
+        if (slot >= job.q_cap) continue;
+        job.prio_q[slot] = it;
+        __threadfence();
+        while (atomicCAS(&job.q_ctr[1], slot, slot + 1) != slot) {}   // publish in reservation order
     }
 }
 
@@ -94,7 +134,7 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
     const int M = P.M, c0 = (M - 1) / 2;
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) *sh_item = atomicAdd(job.ticket, 1);
+        if (threadIdx.x == 0) *sh_item = fetch_item(job);
         __syncthreads();
         const int item = *sh_item;
         if (item >= job.n) break;
@@ -123,12 +163,16 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
             double2 nn = sym_and_norms(c, f, false);
             double ni = nn.y;
             int k = 0, err = 0;
-            bool overflow = false, budget = false;
+            bool overflow = false, budget = false, hot = false;
             while (P.tol_max > ni && ni > P.tol_min) {
                 if (k0 + k >= T.n_tab) { overflow = true; break; }
                 if (c.n_liou > P.max_liouville) { budget = true; break; }
                 f = rg_map_dev<J>(c, f, T, k0 + k, err, ni);
                 ++k; ++n_maps;
+                if (job.row_len > 0 && !hot && c.n_liou > job.hot_threshold) {
+                    hot = true;
+                    if (threadIdx.x == 0) push_neighbours(job, item);
+                }
             }
             if (threadIdx.x == 0) {
                 const bool cv = (ni < P.tol_min) && !overflow && !budget;
@@ -362,12 +406,13 @@ static kern_t pick_kernel(int J) {
 // warps per CTA: one lane per output mode -> ceil(M/32) boxes; rounded up to a multiple of 4 so that the four
 // SM sub-partitions carry the same number of warps (14 warps ran 12 % slower than 16: 4+4+3+3), capped at 16
 // (512 threads x 128 registers = the whole register file).
-static int rg_warps_for(int M) {
+static int rg_warps_for(int M, int J) {
     int w = (((M + 31) / 32 + 3) / 4) * 4;
     if (w < 4) w = 4;
-    if (w > 12) w = 12;   // 384 threads x 168 registers: the convolution loop needs ~150 registers to run spill-free
+    const int wmax = (J >= 8) ? 12 : 8;   // must match __launch_bounds__ of rg_kernel<J>: 384 x 168 regs, or 256 x 128
+    if (w > wmax) w = wmax;
     const char* e = getenv("RG_B200_WARPS");
-    if (e && atoi(e) >= 4 && atoi(e) <= 12 && atoi(e) % 4 == 0) w = atoi(e);
+    if (e && atoi(e) >= 4 && atoi(e) <= wmax && atoi(e) % 4 == 0) w = atoi(e);
     return w;
 }
 
@@ -406,7 +451,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     p->g.init(prm->dim, prm->L, prm->J);
     const rgplan::Geometry& g = p->g;
     std::vector<uint16_t> mask = masks_from_iminus(g, prm->iminus);
-    const int n_warps = rg_warps_for(g.M);
+    const int n_warps = rg_warps_for(g.M, g.J);
     p->hs[0] = rgplan::make_schedule(g, mask, false, false, n_warps);
     p->hs[1] = rgplan::make_schedule(g, mask, true, false, n_warps);
     p->hs[2] = rgplan::make_schedule(g, mask, false, true, n_warps);
@@ -651,11 +696,12 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
 
 extern "C" int rg_region(rg_plan* p, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
                          int32_t* conv, int32_t* count, int32_t* err, rg_stats* stats) {
-    return rg_region_work(p, tab, n, amps, K_flat, nK, conv, count, err, nullptr, stats);
+    return rg_region_work(p, tab, n, amps, K_flat, nK, conv, count, err, nullptr, 0, 0, stats);
 }
 
 extern "C" int rg_region_work(rg_plan* p, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
-                              int32_t* conv, int32_t* count, int32_t* err, int64_t* liouville_per_point, rg_stats* stats) {
+                              int32_t* conv, int32_t* count, int32_t* err, int64_t* liouville_per_point,
+                              int32_t row_len, int32_t hot_threshold, rg_stats* stats) {
     if (!p || !tab || n < 0 || !amps || !K_flat || nK < 1 || !conv || !count || !err) return fail(-1, "bad argument");
     if (p->dp.ct == RG_CT_MULTIPLY && !RG_HAVE_MULTIPLY) return fail(-7, "expm_multiply not available in this build");
     CU(cudaSetDevice(p->device));
@@ -677,6 +723,15 @@ extern "C" int rg_region_work(rg_plan* p, const rg_tables* tab, int32_t n, const
     if ((rc = st.outp(count, sizeof(int) * (size_t)n, &o))) return rc; job.count = (int*)o;
     if ((rc = st.outp(err, sizeof(int) * (size_t)n, &o))) return rc; job.err = (int*)o;
     if (liouville_per_point) { if ((rc = st.outp(liouville_per_point, sizeof(long long) * (size_t)n, &o))) return rc; job.liou_out = (long long*)o; }
+    if (row_len > 0 && n > 0) {
+        // claimed[n] | q_ctr[4] | prio_q[4n], zero-initialised
+        const size_t words = (size_t)n + 4 + 4 * (size_t)n;
+        int* d_sched = nullptr;
+        CU(cudaMalloc(&d_sched, sizeof(int) * words)); st.tmp.push_back(d_sched);
+        CU(cudaMemsetAsync(d_sched, 0, sizeof(int) * words, p->stream));
+        job.claimed = d_sched; job.q_ctr = d_sched + n; job.prio_q = d_sched + n + 4;
+        job.row_len = row_len; job.hot_threshold = hot_threshold > 0 ? hot_threshold : 1500; job.q_cap = 4 * n;
+    }
     if ((rc = launch_job(p, tab->t, job, stats, st))) return rc;
     return st.finish();
 }
@@ -883,7 +938,7 @@ extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_
     if (dim < 1 || dim > 3 || J < 1 || J > 15 || L < 1) return fail(-2, "bad geometry");
     rgplan::Geometry g; g.init(dim, L, J);
     std::vector<uint16_t> mask = masks_from_iminus(g, iminus_wrapped);
-    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, rg_warps_for(g.M));
+    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, rg_warps_for(g.M, g.J));
     if (s.n_warps < 0) return fail(-5, "too many output modes for one CTA's convolution schedule");
     *n_warps = s.n_warps; *n_boxes = s.n_boxes; *n_entries = (int)s.entries.size() / 2; *n_support = s.n_support;
     if (cost) { cost[0] = s.fma_useful; cost[1] = s.fma_executed; cost[2] = s.cost_max; cost[3] = s.cost_total; }

@@ -479,10 +479,12 @@ class RG:
             out.append(int(k[0]) * self._M + int(xp.ravel_multi_index(tuple(xp.mod(k[1:], n1)), self.r_jl[1:])))
         return xp.array(out, dtype=xp.int32)
 
-    def points(self, amps, conv=None, count=None, err=None, work=None):
+    def points(self, amps, conv=None, count=None, err=None, work=None, row_len=0, hot_threshold=0):
         """`point` for a batch: amps[B, len(K)] (host ndarray, pinned torch tensor or CUDA tensor).
         Returns (conv, count, error) int32 arrays (or fills the supplied host/device buffers).
-        `work`: optional int64[B] buffer receiving the liouville evaluations spent on each point."""
+        `work`: optional int64[B] buffer receiving the liouville evaluations spent on each point.
+        `row_len` > 0: the batch is a row-major grid with rows of that length; heavy points then pull their
+        grid neighbours forward in the device work queue (load balance only, results are unchanged)."""
         if isinstance(amps, xp.ndarray):
             amps = _f64(amps)
             n = amps.shape[0]
@@ -495,5 +497,5 @@ class RG:
         nrm, onu, oms, tab = self._tables(self.Omega)
         kf = self.K_flat()
         _lib.check(_lib.lib().rg_region_work(self._plan(), tab, n, _ptr(amps), kf.ctypes.data, nK, _ptr(conv), _ptr(count),
-                                             _ptr(err), _ptr(work), self._stats()))
+                                             _ptr(err), _ptr(work), int(row_len), int(hot_threshold), self._stats()))
         return conv, count, err

@@ -22,4 +22,5 @@ print("errors", dict(zip(*np.unique(err, return_counts=True))))
 order = np.argsort(-work)[:12]
 for i in order:
     print("  pt %5d x=%.5f y=%.5f work %8d conv %d count %3d err %d" % (i, amps[i, 0], amps[i, 1], work[i], conv[i], count[i], err[i]))
+np.savez_compressed(os.path.join("gpurun_out", "work_%s_%d.npz" % (ct, n)), work=work, conv=conv, count=count, err=err, amps=amps)
 print("work percentiles", np.percentile(work, [50, 90, 99, 99.9]).astype(int))
