@@ -194,7 +194,8 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
 #pragma unroll
     for (int k = 0; k < R::NPAD; ++k) {
         const double2 t = yq[k % R::YW];
-        if (k == 1 && more) decode_entry(q, me, i_next, gp_n, yp_n, jm_n);   // after the first block has issued
+        if (k == 1) decode_entry(q, me, i_next & 31, gp_n, yp_n, jm_n);   // after the first block has issued; past the
+                                                                        // chunk end this reads a valid dummy entry
         if (k + R::YW < R::NPAD) yq[k % R::YW] = lds128(yp + 16 * R::unit(k + R::YW));
         else yq[k % R::YW] = lds128(yp_n + 16 * R::unit(k + R::YW - R::NPAD));
         if (k >= R::NP) continue;   // padding pair
@@ -239,7 +240,7 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     for (int u = 0; u < R::ND2; ++u) { const double2 t = lds128(gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
     uint32_t gp_n = gp, yp_n = yp;
     int jm_n = jm;
-    if (more) decode_entry(q, me, i_next, gp_n, yp_n, jm_n);
+    decode_entry(q, me, i_next & 31, gp_n, yp_n, jm_n);
     // conv(dA y, Omega g): y1[j1] = (j1+1) y[j1+1] is non-zero iff j1+1 < jm
 #pragma unroll
     for (int k = 0; k < R::NP1; ++k) {
