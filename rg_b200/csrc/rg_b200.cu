@@ -44,6 +44,7 @@ struct Job {
     int mode;  // 0 region (amps), 1 converge (f given), 2 rg_map x n_iter, 3 expm, 4 liouville, 5 generate_y, 6 compute_m_s
     int n;
     int sched;  // 0 sparse, 1 dense (2 = sparse half-space is selected on the device)
+    int csize;  // thread-block cluster size: 1, 2 or 4 CTAs per Hamiltonian (modes 0-2 only)
     int* ticket;
     // inputs
     const double* amps; const int* K_flat; int nK;   // mode 0 (K_flat: j*M + centred mode)
@@ -117,9 +118,13 @@ __device__ void push_neighbours(const Job& job, int item) {
 
 template <int J>
 __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_kernel(const int slot, const __grid_constant__ Tables T, const __grid_constant__ Job job) {
+    namespace cg = cooperative_groups;
     Ctx c;
     c.slot = slot;
     c.sidx = job.sched;
+    c.csize = job.csize;
+    c.cbase = job.csize == 4 ? 6 : (job.csize == 2 ? 3 : 0);
+    c.crank = job.csize > 1 ? (int)cg::this_cluster().block_rank() : 0;
     const DevPlan& P = RG_PLAN(c);
     const Smem sm = smem_view(P, RG_SCHED(c));
     int* sh_item = reinterpret_cast<int*>(sm.red + 64);
@@ -133,9 +138,20 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
     double* fa = c.ws + (size_t)WS_FA * P.vecjl;
     const int M = P.M, c0 = (M - 1) / 2;
     for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) *sh_item = fetch_item(job);
-        __syncthreads();
+        if (c.csize > 1) {
+            // one ticket per cluster: rank 0 draws it and posts it into every peer's shared memory
+            cg::cluster_group cl = cg::this_cluster();
+            cl.sync();
+            if (c.crank == 0 && threadIdx.x == 0) {
+                const int it = fetch_item(job);
+                for (int r = 0; r < c.csize; ++r) *cl.map_shared_rank(sh_item, r) = it;
+            }
+            cl.sync();
+        } else {
+            __syncthreads();
+            if (threadIdx.x == 0) *sh_item = fetch_item(job);
+            __syncthreads();
+        }
         const int item = *sh_item;
         if (item >= job.n) break;
         c.n_liou = 0; c.n_lie = 0; c.symm = 0; c.t_conv = 0; c.t_epi = 0;
@@ -171,10 +187,10 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
                 ++k; ++n_maps;
                 if (job.row_len > 0 && !hot && c.n_liou > job.hot_threshold) {
                     hot = true;
-                    if (threadIdx.x == 0) push_neighbours(job, item);
+                    if (threadIdx.x == 0 && c.crank == 0) push_neighbours(job, item);
                 }
             }
-            if (threadIdx.x == 0) {
+            if (threadIdx.x == 0 && c.crank == 0) {
                 const bool cv = (ni < P.tol_min) && !overflow && !budget;
                 job.conv[item] = cv ? 1 : 0;
                 job.count[item] = cv ? -k : k;
@@ -191,8 +207,10 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
                 ++n_maps;
             }
             __syncthreads();
-            store_wrapped(P, f, job.f_out + (size_t)item * P.vecjl);
-            if (threadIdx.x == 0) job.err[item] = err;
+            if (c.crank == 0) {
+                store_wrapped(P, f, job.f_out + (size_t)item * P.vecjl);
+                if (threadIdx.x == 0) job.err[item] = err;
+            }
         } else if (job.mode == 3 || job.mode == 4) {
             // caller-supplied y (wrapped) -> WS_Y1..3
             c.Omega_nu = job.Omega_nu;
@@ -241,8 +259,8 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
             store_wrapped(P, c.ws + (size_t)WS_Y3 * P.vecjl, job.y3_out + (size_t)item * P.vecjl);
             if (threadIdx.x == 0) job.y0_out[item] = a;
         }
-        if (threadIdx.x == 0 && job.liou_out) job.liou_out[item] = c.n_liou;
-        if (threadIdx.x == 0 && job.n_liou) {
+        if (threadIdx.x == 0 && c.crank == 0 && job.liou_out) job.liou_out[item] = c.n_liou;
+        if (threadIdx.x == 0 && c.crank == 0 && job.n_liou) {
             job.n_liou[item] = c.n_liou; job.n_lie[item] = c.n_lie; job.n_maps[item] = n_maps;
             job.n_maps[(size_t)job.n + item] = c.t_conv; job.n_maps[2 * (size_t)job.n + item] = c.t_epi;
             job.n_maps[3 * (size_t)job.n + item] = clock64() - t_item;
@@ -354,8 +372,10 @@ struct DevSched {
 
 struct rg_plan {
     rgplan::Geometry g;
-    rgplan::Schedule hs[3];
-    DevSched ds[3];
+    rgplan::Schedule hs[9];   // kind + 3*log2(csize)
+    DevSched ds[9];
+    int cluster_pref = 0;     // 0 = automatic, else forced cluster size for the fused modes
+    int max_cluster = 1;      // largest cluster size the device can co-schedule for this kernel
     DevPlan dp;
     int device = 0;
     int slot = -1;  // index into the constant-memory plan table
@@ -452,15 +472,18 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     const rgplan::Geometry& g = p->g;
     std::vector<uint16_t> mask = masks_from_iminus(g, prm->iminus);
     const int n_warps = rg_warps_for(g.M, g.J);
-    p->hs[0] = rgplan::make_schedule(g, mask, false, false, n_warps);
-    p->hs[1] = rgplan::make_schedule(g, mask, true, false, n_warps);
-    p->hs[2] = rgplan::make_schedule(g, mask, false, true, n_warps);
+    for (int ci = 0; ci < 3; ++ci) {
+        const int vw = n_warps << ci;   // virtual warps of a cluster of 1, 2, 4 CTAs
+        p->hs[3 * ci + 0] = rgplan::make_schedule(g, mask, false, false, vw, 1 << ci);
+        p->hs[3 * ci + 1] = rgplan::make_schedule(g, mask, true, false, vw, 1 << ci);
+        p->hs[3 * ci + 2] = rgplan::make_schedule(g, mask, false, true, vw, 1 << ci);
+    }
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, p->device));
     p->sm_count = prop.multiProcessorCount;
     p->threads = n_warps * 32;
-    for (int s = 0; s < 3; ++s)
-        if (p->hs[s].n_warps != n_warps) { delete p; return fail(-5, "too many output modes for one CTA's convolution schedule"); }
+    for (int s = 0; s < 9; ++s)
+        if (p->hs[s].n_warps != (n_warps << (s / 3))) { delete p; return fail(-5, "too many output modes for one CTA's convolution schedule"); }
     DevPlan& dp = p->dp;
     memset(&dp, 0, sizeof(dp));
     dp.dim = g.dim; dp.L = g.L; dp.J = g.J; dp.JP = g.JP; dp.n1 = g.n1; dp.M = g.M; dp.vecjl = g.vecjl;
@@ -500,7 +523,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     if ((rc = dev_upload(p, prm->theta, (size_t)prm->n_theta, &d_theta))) return rc;
     dp.omega0_nu = d_om0; dp.mask = d_mask; dp.reidx = d_reidx; dp.normw = d_normw; dp.c2w = d_c2w;
     dp.theta = d_theta; dp.n_theta = prm->n_theta;
-    for (int s = 0; s < 3; ++s) {
+    for (int s = 0; s < 9; ++s) {
         const rgplan::Schedule& hs = p->hs[s];
         DevSched& ds = p->ds[s];
         if ((rc = dev_upload(p, hs.lane_out.data(), hs.lane_out.size(), &ds.lane_out))) return rc;
@@ -510,6 +533,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
         if ((rc = dev_upload(p, hs.supp_rec.data(), hs.supp_rec.size(), &ds.supp_rec))) return rc;
         dp.sched[s].n_warps = hs.n_warps; dp.sched[s].n_support = hs.n_support;
         dp.sched[s].n_boxes = hs.n_boxes; dp.sched[s].max_rank = hs.max_rank; dp.sched[s].half = hs.half ? 1 : 0;
+        for (int r = 0; r < 4; ++r) { dp.sched[s].fin_begin[r] = hs.fin_begin[r]; dp.sched[s].fin_end[r] = hs.fin_end[r]; }
         dp.sched[s].lane_out = ds.lane_out; dp.sched[s].lane_coord = ds.lane_coord; dp.sched[s].pieces = ds.pieces;
         dp.sched[s].entries = ds.entries; dp.sched[s].supp_rec = ds.supp_rec;
     }
@@ -535,6 +559,21 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     p->slot = alloc_slot();
     if (p->slot < 0) { rg_plan_destroy(p); return fail(-8, "too many live plans (max " + std::to_string(RG_MAX_PLANS) + " per process)"); }
     CU(cudaMemcpyToSymbol(c_plan, &p->dp, sizeof(DevPlan), sizeof(DevPlan) * (size_t)p->slot));
+    // largest cluster the device co-schedules with this kernel's footprint
+    p->max_cluster = 1;
+    for (int cs = 2; cs <= 4; cs *= 2) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(cs * p->sm_count); cfg.blockDim = dim3(p->threads); cfg.dynamicSmemBytes = p->smem[0];
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = cs; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, p->kernel, &cfg) == cudaSuccess && ncl * cs * 10 >= p->grid_max[0] * 8) p->max_cluster = cs;
+        else { cudaGetLastError(); break; }
+    }
+    if (getenv("RG_B200_CLUSTER")) p->cluster_pref = atoi(getenv("RG_B200_CLUSTER"));
     p->ws_ctas = (size_t)std::max(p->grid_max[0], p->grid_max[1]);
     CU(cudaMalloc(&p->ws, p->ws_ctas * WS_COUNT * g.vecjl * sizeof(double)));
     CU(cudaMemset(p->ws, 0, p->ws_ctas * WS_COUNT * g.vecjl * sizeof(double)));
@@ -662,10 +701,31 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     CU(cudaMemsetAsync(p->ticket, 0, sizeof(int), p->stream));
     job.ticket = p->ticket;
     job.ws_base = p->ws;
-    const int grid = std::max(1, std::min(job.n, p->grid_max[s]));
+    // Cluster size: a Hamiltonian owned by a pair (quad) of CTAs finishes 1.46x (1.9x) sooner but at 0.73 (0.48)
+    // of the per-SM throughput (the epilogue is replicated, whole boxes balance to 4:3), so clusters are used
+    // only when there are fewer Hamiltonians than SMs: compute_line, approach, small surfaces.
+    int csize = 1;
+    if (job.mode <= 2 && p->max_cluster > 1) {
+        if (p->cluster_pref > 0) csize = std::min(p->cluster_pref, p->max_cluster);
+        else if ((long long)job.n * 4 <= p->grid_max[s]) csize = std::min(4, p->max_cluster);
+        else if ((long long)job.n * 2 <= p->grid_max[s]) csize = 2;
+    }
+    job.csize = csize;
+    int grid = std::max(1, std::min(job.n, p->grid_max[s] / csize)) * csize;
     kern_t k = (kern_t)p->kernel;
     CU(cudaEventRecord(p->ev0, p->stream));
-    k<<<grid, p->threads, p->smem[s], p->stream>>>(p->slot, T, job);
+    if (csize == 1) {
+        k<<<grid, p->threads, p->smem[s], p->stream>>>(p->slot, T, job);
+    } else {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(p->threads); cfg.dynamicSmemBytes = p->smem[s]; cfg.stream = p->stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        CU(cudaLaunchKernelEx(&cfg, k, p->slot, T, job));
+    }
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev1, p->stream));
     if (stats) {

@@ -7,6 +7,7 @@
 // fuse, the elementwise arithmetic rounds like the reference's numpy expressions.
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <stdint.h>
 
 namespace rgdev {
@@ -14,6 +15,7 @@ namespace rgdev {
 #define RG_MAXP 4   // pieces per warp (rgplan::MAXP)
 struct Sched {
     int n_warps, n_boxes, n_support, max_rank, half;
+    int fin_begin[4], fin_end[4];   // boxes owned by each CTA of a cluster
     const int* lane_out;         // [NB*32] centred mode of each lane, -1 idle
     const uint32_t* lane_coord;  // [NB*32] packed biased coords
     const int4* pieces;          // [NW*RG_MAXP] {box, begin, end, rank}; box = -1 unused; heads first
@@ -40,8 +42,9 @@ struct DevPlan {
     const int* c2w;           // [M] centred -> wrapped index
     const double* theta;
     int n_theta;
-    Sched sched[3];           // 0: I^- support, all modes; 1: dense (caller-supplied y); 2: I^- support, half
-                              // space only (exactly symmetric operands: out[-nu] = out[nu])
+    // schedule kind: 0 = I^- support, all modes; 1 = dense (caller-supplied y); 2 = I^- support, half space only
+    // (exactly symmetric operands: out[-nu] = out[nu]).  One set per cluster size 1, 2, 4: index kind + 3*log2(csize).
+    Sched sched[9];
 };
 
 // workspace arrays of one CTA (each vecjl doubles, layout [j][centred nu])
@@ -58,6 +61,8 @@ struct Ctx {
     int slot;     // index into c_plan
     int sidx;     // schedule index (0 sparse, 1 dense, 2 sparse half-space)
     int symm;     // 1 while the coefficient array is exactly symmetric under nu -> -nu (after RG.sym)
+    int cbase;    // 3*log2(cluster size): offset of the schedule set
+    int csize, crank;  // thread-block cluster size (1, 2, 4) and this CTA's rank in it
     double* ws;   // this CTA's global workspace
     const double* Omega_nu;  // current Omega.nu, centred, global
     long long n_liou, n_lie;
@@ -80,7 +85,7 @@ __device__ __forceinline__ Smem smem_view(const DevPlan& P, const Sched& S) {
     return v;
 }
 #define RG_PLAN(c) c_plan[(c).slot]
-#define RG_SCHED(c) c_plan[(c).slot].sched[(c).sidx]
+#define RG_SCHED(c) c_plan[(c).slot].sched[(c).sidx + (c).cbase]
 
 __device__ __forceinline__ double pmax(double a, double b) { return (a > b || a != a) ? a : b; }
 
@@ -325,19 +330,28 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
 // Every warp owns up to RG_MAXP pieces of the boxes' source lists: heads (rank 0) are stored as they
 // finish, the single continuation a warp may hold (rank r > 0) is added in phase r -- a fixed order, so
 // the result does not depend on timing.  On the half-space schedule only modes nu <= 0 are produced.
+//
+// Cluster mode (csize = 2 or 4 CTAs per Hamiltonian): every CTA of the cluster runs the whole program on
+// its own copy of the state (bit-identical control flow); only this function is split.  The planner gives
+// each CTA a contiguous group of whole boxes, CTA r computes them exactly as above with its own warps
+// (virtual warps [r*W, (r+1)*W)) and then broadcasts the finished rows into the `out` buffer of every peer
+// through distributed shared memory: two cluster barriers and (csize-1) x its share of `out` per term.
 template <int J>
 __device__ __noinline__ void conv_all(Ctx& c) {
     constexpr int JP = J + 1;
+    namespace cg = cooperative_groups;
     const Sched& S = RG_SCHED(c);
     double* const out = smem_view(RG_PLAN(c), S).out;
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwc = (int)(blockDim.x >> 5);
+    const int vw = c.crank * nwc + w;
     const long long t_begin = clock64();
+    if (c.csize > 1) cg::this_cluster().sync();   // every peer has finished reading its `out` of the previous term
     double acc[JP];
     int4 held = make_int4(-1, 0, 0, 0);
-    if (w < S.n_warps) {
+    if (vw < S.n_warps) {
 #pragma unroll 1
         for (int q = 0; q < RG_MAXP; ++q) {
-            const int4 p = S.pieces[w * RG_MAXP + q];
+            const int4 p = S.pieces[vw * RG_MAXP + q];
             if (p.x < 0) continue;
             if (p.w > 0) { held = p; continue; }
             conv_piece<J>(c, p.x, p.y, p.z, acc);
@@ -359,6 +373,23 @@ __device__ __noinline__ void conv_all(Ctx& c) {
             }
         }
         __syncthreads();
+    }
+    if (c.csize > 1) {
+        cg::cluster_group cl = cg::this_cluster();
+        for (int b = S.fin_begin[c.crank] + w; b < S.fin_end[c.crank]; b += nwc) {
+            const int nu = S.lane_out[b * 32 + lane];
+            if (nu < 0) continue;
+            double v[JP];
+#pragma unroll
+            for (int j = 0; j < JP; ++j) v[j] = out[nu * JP + j];
+            for (int r = 0; r < c.csize; ++r) {
+                if (r == c.crank) continue;
+                double* o = cl.map_shared_rank(out, r) + nu * JP;
+#pragma unroll
+                for (int j = 0; j < JP; ++j) o[j] = v[j];
+            }
+        }
+        cl.sync();
     }
     c.n_liou++;
     c.t_conv += clock64() - t_begin;

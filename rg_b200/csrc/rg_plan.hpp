@@ -66,7 +66,9 @@ struct Piece { int box, begin, end, rank; };  // rank: position of the piece wit
 constexpr int MAXP = 4;  // pieces per warp: any number of heads (rank 0) up to MAXP-1, at most one continuation
 
 struct Schedule {
-    int n_warps = 0;    // warps per CTA (pieces are dealt to these)
+    int n_warps = 0;    // warps of the cluster (csize CTAs x warps per CTA); pieces are dealt to these
+    int csize = 1;      // CTAs per Hamiltonian
+    int fin_begin[4] = {0, 0, 0, 0}, fin_end[4] = {0, 0, 0, 0};   // boxes owned (computed and broadcast) by each CTA
     int n_boxes = 0;    // groups of <= 32 output modes
     int n_support = 0;
     int max_rank = 0;
@@ -84,7 +86,8 @@ struct Schedule {
 
 // mask[c] = bit j set iff (j, nu_c) in I^- (centred order).  dense: every mode, every level (jm = J+2 so
 // that the y1[J] term of a caller-supplied generator is kept).  half: only modes c <= centre are computed.
-inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& mask, bool dense, bool half, int n_warps) {
+// n_warps: warps of the whole cluster (csize CTAs x warps per CTA).
+inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& mask, bool dense, bool half, int n_warps, int csize = 1) {
     Schedule s;
     const int M = g.M, L = g.L, J = g.J, c0 = (M - 1) / 2;
     s.half = half;
@@ -149,46 +152,77 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
     // entries with every Taylor level present first: the branch-free path then runs in long stretches
     for (int b = 0; b < NB; ++b)
         std::stable_sort(lists[b].begin(), lists[b].end(), [&](int x, int y) { return (s.jm[x] == g.JP) > (s.jm[y] == g.JP); });
-    // ---- deal the concatenated lists to the warps in equal-cost segments.  A warp's segment starts with at
-    // most one continuation of a box (rank > 0) followed by heads of later boxes (rank 0).
+    // ---- cluster mode: whole boxes are first partitioned over the `csize` CTAs of a cluster (contiguous
+    // groups, minimal maximum cost) so that every partial sum of a box stays inside one CTA; only the final
+    // rows of a box travel through distributed shared memory.
+    std::vector<int64_t> bcost(NB, 0);
+    auto tcost = [&](int c1) { return (int64_t)taylor_fma(std::min<int>(s.jm[c1], g.JP), J) + (s.jm[c1] > g.JP ? 1 : 0); };
+    for (int b = 0; b < NB; ++b) for (int c1 : lists[b]) bcost[b] += tcost(c1);
+    std::vector<int> gbeg(csize + 1, 0);
+    {
+        // optimal contiguous partition by binary search on the bottleneck
+        int64_t lo = 0, hi = 0;
+        for (int b = 0; b < NB; ++b) { lo = std::max(lo, bcost[b]); hi += bcost[b]; }
+        auto fits = [&](int64_t cap, std::vector<int>* cuts) {
+            int parts = 1; int64_t cur = 0;
+            if (cuts) { cuts->assign(csize + 1, NB); (*cuts)[0] = 0; }
+            for (int b = 0; b < NB; ++b) {
+                if (cur + bcost[b] > cap && cur > 0) { if (parts >= csize) return false; if (cuts) (*cuts)[parts] = b; ++parts; cur = 0; }
+                cur += bcost[b];
+            }
+            return true;
+        };
+        while (lo < hi) { int64_t mid = (lo + hi) / 2; if (fits(mid, nullptr)) hi = mid; else lo = mid + 1; }
+        fits(lo, &gbeg);
+        gbeg[csize] = NB;
+    }
+    s.csize = csize;
+    for (int r = 0; r < 4; ++r) { s.fin_begin[r] = r < csize ? gbeg[r] : NB; s.fin_end[r] = r < csize ? gbeg[r + 1] : NB; }
+    // ---- inside every CTA: deal the concatenated lists of its boxes to its warps in equal-cost segments.  A
+    // warp's segment starts with at most one continuation of a box (rank > 0) followed by heads of later boxes.
+    const int NWc = NW / csize;
     s.pieces.assign(NW * MAXP, Piece{-1, 0, 0, 0});
     std::vector<int> npieces(NW, 0);
     std::vector<int64_t> wcost(NW, 0);
-    auto tcost = [&](int c1) { return (int64_t)taylor_fma(std::min<int>(s.jm[c1], g.JP), J) + (s.jm[c1] > g.JP ? 1 : 0); };
-    int w = 0;
-    int64_t acc = 0;
-    for (int b = 0; b < NB; ++b) {
-        int rank = 0;
-        size_t k = 0;
-        do {
-            // open a piece of box b on warp w
-            while (w < NW - 1 && (npieces[w] >= MAXP || (rank > 0 && npieces[w] > 0) ||
-                                  acc * NW >= total * (int64_t)(w + 1))) ++w;
-            Piece pc{b, (int)s.entries.size() / 2, 0, rank};
-            while (k < lists[b].size()) {
-                const int c1 = lists[b][k];
-                if (w < NW - 1 && acc * NW >= total * (int64_t)(w + 1) && (int)s.entries.size() / 2 > pc.begin) break;
-                int v1[4]; g.coords(c1, v1);
-                // word0: biased coords (validity test) | jm<<24 ; word1: centred linear index | record<<16
-                s.entries.push_back(g.pack(v1) | ((uint32_t)s.jm[c1] << 24));
-                s.entries.push_back((uint32_t)c1 | ((uint32_t)s.supp_rec[c1] << 16));
-                acc += tcost(c1); wcost[w] += tcost(c1);
-                ++k;
-            }
-            pc.end = (int)s.entries.size() / 2;
-            if (npieces[w] >= MAXP) { s.n_warps = -1; return s; }   // too many boxes for this CTA; reported by the caller
-            // heads first, the continuation (if any) last
-            if (rank == 0) {
-                int q = npieces[w];
-                if (q > 0 && s.pieces[w * MAXP + q - 1].rank > 0) { s.pieces[w * MAXP + q] = s.pieces[w * MAXP + q - 1]; s.pieces[w * MAXP + q - 1] = pc; }
-                else s.pieces[w * MAXP + q] = pc;
-            } else {
-                s.pieces[w * MAXP + npieces[w]] = pc;
-            }
-            ++npieces[w];
-            s.max_rank = std::max(s.max_rank, rank);
-            ++rank;
-        } while (k < lists[b].size());
+    for (int r = 0; r < csize; ++r) {
+        int64_t gtotal = 0;
+        for (int b = gbeg[r]; b < gbeg[r + 1]; ++b) gtotal += bcost[b];
+        const int w0 = r * NWc, w1 = w0 + NWc;
+        int w = w0;
+        int64_t acc = 0;
+        for (int b = gbeg[r]; b < gbeg[r + 1]; ++b) {
+            int rank = 0;
+            size_t k = 0;
+            do {
+                // open a piece of box b on warp w
+                while (w < w1 - 1 && (npieces[w] >= MAXP || (rank > 0 && npieces[w] > 0) ||
+                                      acc * NWc >= gtotal * (int64_t)(w - w0 + 1))) ++w;
+                Piece pc{b, (int)s.entries.size() / 2, 0, rank};
+                while (k < lists[b].size()) {
+                    const int c1 = lists[b][k];
+                    if (w < w1 - 1 && acc * NWc >= gtotal * (int64_t)(w - w0 + 1) && (int)s.entries.size() / 2 > pc.begin) break;
+                    int v1[4]; g.coords(c1, v1);
+                    // word0: biased coords (validity test) | jm<<24 ; word1: centred linear index | record<<16
+                    s.entries.push_back(g.pack(v1) | ((uint32_t)s.jm[c1] << 24));
+                    s.entries.push_back((uint32_t)c1 | ((uint32_t)s.supp_rec[c1] << 16));
+                    acc += tcost(c1); wcost[w] += tcost(c1);
+                    ++k;
+                }
+                pc.end = (int)s.entries.size() / 2;
+                if (npieces[w] >= MAXP) { s.n_warps = -1; return s; }   // too many boxes for this CTA; reported by the caller
+                // heads first, the continuation (if any) last
+                if (rank == 0) {
+                    int q = npieces[w];
+                    if (q > 0 && s.pieces[w * MAXP + q - 1].rank > 0) { s.pieces[w * MAXP + q] = s.pieces[w * MAXP + q - 1]; s.pieces[w * MAXP + q - 1] = pc; }
+                    else s.pieces[w * MAXP + q] = pc;
+                } else {
+                    s.pieces[w * MAXP + npieces[w]] = pc;
+                }
+                ++npieces[w];
+                s.max_rank = std::max(s.max_rank, rank);
+                ++rank;
+            } while (k < lists[b].size());
+        }
     }
     for (int i = 0; i < NW; ++i) { s.cost_max = std::max(s.cost_max, wcost[i]); }
     s.cost_total = total;
