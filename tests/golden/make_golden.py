@@ -177,9 +177,9 @@ def main(argv):
         # heavier secondary grid (richer boundary), 12x12 on [0,0.06]x[0,0.08] at L=J=10
         region_fixture("region_L10J10_12x12_expm_onestep", dict(L=10, J=10, CT="expm_onestep"),
                        np.linspace(0, 0.06, 12), np.linspace(0, 0.08, 12))
-    if "line" in what:
+    if "line" in what or "line10" in what:
         RG, RG_modules, RG_dict = ref_loader.load()
-        for L, rd in ((5, 1e-8),):
+        for L, rd in ((5, 1e-8),) + (((10, 1e-8),) if "line10" in what else ()):
             case = _mk_case(dict(L=L, J=L, CT="expm_onestep", RelDist=rd))
             import io, contextlib
             with contextlib.redirect_stdout(io.StringIO()):
