@@ -79,6 +79,7 @@ typedef struct {
     int64_t clk_conv;          /* SM clocks inside the bracket convolution, summed over Hamiltonians */
     int64_t clk_epilogue;      /* SM clocks inside the series epilogue (update + norms), summed */
     int64_t clk_total;         /* SM clocks from ticket to result, summed over Hamiltonians */
+    int64_t clk_conv_busy;     /* of clk_conv: clocks warp 0 spent on its own pieces (the rest is barrier wait) */
     float kernel_ms;           /* device time of the last batched call (CUDA events on the plan's stream) */
     int32_t launches;          /* kernels launched by the last call */
 } rg_stats;

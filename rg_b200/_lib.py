@@ -34,6 +34,7 @@ class RGStats(ctypes.Structure):
     _fields_ = [("liouville", ctypes.c_int64), ("lie_steps", ctypes.c_int64), ("rg_maps", ctypes.c_int64),
                 ("conv_fma_executed", ctypes.c_int64), ("conv_fma_useful", ctypes.c_int64),
                 ("clk_conv", ctypes.c_int64), ("clk_epilogue", ctypes.c_int64), ("clk_total", ctypes.c_int64),
+                ("clk_conv_busy", ctypes.c_int64),
                 ("kernel_ms", ctypes.c_float), ("launches", ctypes.c_int32)]
 
 

@@ -154,7 +154,7 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
         }
         const int item = *sh_item;
         if (item >= job.n) break;
-        c.n_liou = 0; c.n_lie = 0; c.symm = 0; c.t_conv = 0; c.t_epi = 0;
+        c.n_liou = 0; c.n_lie = 0; c.symm = 0; c.t_conv = 0; c.t_epi = 0; c.t_busy = 0;
         const long long t_item = clock64();
         c.rng = 0x243F6A8885A308D3ull ^ ((uint64_t)(item + 1) * 0x9E3779B97F4A7C15ull);
         long long n_maps = 0;
@@ -264,6 +264,7 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
             job.n_liou[item] = c.n_liou; job.n_lie[item] = c.n_lie; job.n_maps[item] = n_maps;
             job.n_maps[(size_t)job.n + item] = c.t_conv; job.n_maps[2 * (size_t)job.n + item] = c.t_epi;
             job.n_maps[3 * (size_t)job.n + item] = clock64() - t_item;
+            job.n_maps[4 * (size_t)job.n + item] = c.t_busy;
         }
     }
 }
@@ -694,9 +695,9 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     const rgplan::Geometry& g = p->g;
     long long* d_cnt = nullptr;
     if (stats) {
-        CU(cudaMalloc(&d_cnt, sizeof(long long) * 6 * (size_t)std::max(job.n, 1)));
+        CU(cudaMalloc(&d_cnt, sizeof(long long) * 7 * (size_t)std::max(job.n, 1)));
         st.tmp.push_back(d_cnt);
-        CU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 6 * (size_t)std::max(job.n, 1), p->stream));
+        CU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 7 * (size_t)std::max(job.n, 1), p->stream));
         job.n_liou = d_cnt; job.n_lie = d_cnt + job.n; job.n_maps = d_cnt + 2 * (size_t)job.n;
     }
     CU(cudaMemsetAsync(p->ticket, 0, sizeof(int), p->stream));
@@ -730,7 +731,7 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev1, p->stream));
     if (stats) {
-        std::vector<long long> h(6 * (size_t)std::max(job.n, 1));
+        std::vector<long long> h(7 * (size_t)std::max(job.n, 1));
         CU(cudaMemcpyAsync(h.data(), d_cnt, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
         memset(stats, 0, sizeof(*stats));
@@ -738,6 +739,7 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
             stats->liouville += h[i]; stats->lie_steps += h[job.n + i]; stats->rg_maps += h[2 * (size_t)job.n + i];
             stats->clk_conv += h[3 * (size_t)job.n + i]; stats->clk_epilogue += h[4 * (size_t)job.n + i];
             stats->clk_total += h[5 * (size_t)job.n + i];
+            stats->clk_conv_busy += h[6 * (size_t)job.n + i];
         }
         // fused modes run the half-space schedule for the series (the 1-norm estimator of expm_multiply runs
         // the full one; its share is accounted at the half-space cost, i.e. under-counted)

@@ -69,6 +69,7 @@ struct Ctx {
     long long n_liou, n_lie;
     uint64_t rng;  // state of the 1-norm estimator's +-1 columns (seeded per Hamiltonian)
     long long t_conv, t_epi;  // SM clocks spent in conv_all / series_epilogue (thread 0's view; profiling aid)
+    long long t_busy;         // of t_conv: clocks warp 0 spent computing its own pieces (the rest is barrier wait)
 };
 
 struct Smem {
@@ -353,6 +354,7 @@ __device__ __noinline__ void conv_all(Ctx& c) {
     for (int st = 0; st < S.n_stages; ++st) {
         const int4* pieces = S.pieces + (size_t)st * S.n_warps * RG_MAXP;
         int4 held = make_int4(-1, 0, 0, 0);
+        const long long t_stage = clock64();
         if (vw < S.n_warps) {
 #pragma unroll 1
             for (int q = 0; q < RG_MAXP; ++q) {
@@ -373,6 +375,7 @@ __device__ __noinline__ void conv_all(Ctx& c) {
             }
             if (held.x >= 0) conv_piece<J>(c, held.x, held.y, held.z, acc);
         }
+        c.t_busy += clock64() - t_stage;
         __syncthreads();
         for (int r = 1; r <= S.max_rank[st]; ++r) {
             if (held.x >= 0 && held.w == r) {

@@ -30,5 +30,5 @@ for rep in range(int(os.environ.get('PROBE_REPS', '2'))):
           % (len(amps), dt, st.kernel_ms, len(amps) / (st.kernel_ms * 1e-3), st.liouville, st.liouville / len(amps), st.lie_steps, st.rg_maps,
              fl_useful / st.kernel_ms * 1e-9, fl_exec / st.kernel_ms * 1e-9, st.liouville * 28.924e6 / st.kernel_ms * 1e-9,
              st.kernel_ms * 1e3 * 148 * info['ctas_per_sm'] / max(st.liouville, 1)))
-    print("   clocks per liouville: conv %.0f  epilogue %.0f  total %.0f" % (st.clk_conv / max(st.liouville, 1), st.clk_epilogue / max(st.liouville, 1), st.clk_total / max(st.liouville, 1)))
+    print("   clocks per liouville: conv %.0f (warp 0 busy %.0f)  epilogue %.0f  total %.0f" % (st.clk_conv / max(st.liouville, 1), st.clk_conv_busy / max(st.liouville, 1), st.clk_epilogue / max(st.liouville, 1), st.clk_total / max(st.liouville, 1)))
 print("converged %d, errors %s" % (conv.sum(), dict(zip(*np.unique(err, return_counts=True)))))
