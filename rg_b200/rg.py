@@ -385,6 +385,28 @@ class RG:
         ndarray to `sym`, quirk Q1); the finite-difference Jacobian itself is out of scope of this path."""
         raise AttributeError("'numpy.ndarray' object has no attribute 'f'")
 
+    def jacobian(self, h, dx, columns=None):
+        """The finite-difference Jacobian RG.eigenvalues intends (RG.py:231-239), as one batch of rg_maps:
+        row _ = (rg_map(h + sym(dx e_)).f - h.f) / dx.  `columns` restricts the rows computed."""
+        n = int(self.vecjl)
+        idx = xp.arange(n) if columns is None else xp.asarray(columns, dtype=int)
+        delta = xp.zeros((len(idx), n))
+        delta[xp.arange(len(idx)), idx] = dx
+        sdelta = xp.empty_like(delta)
+        _lib.check(_lib.lib().rg_sym(self._plan(), len(idx), delta.ctypes.data, sdelta.ctypes.data))
+        f = _f64(h.f).reshape(-1)
+        f_out, err = self.rg_map_batch(f[None, :] + sdelta, h.Omega, n_iter=1)
+        return (f_out.reshape(len(idx), n) - f[None, :]) / dx
+
+    def eigenvalues_batched(self, h, dx, n=1):
+        """What RG.eigenvalues (RG.py:230-242) is meant to return -- the n largest-modulus eigenvalues of the
+        finite-difference Jacobian of the RG map -- computed as vecjl independent rg_maps in one GPU batch.
+        (The reference's own method raises on every call, quirk Q1; `eigenvalues` keeps that behaviour.)"""
+        jac = self.jacobian(h, dx)
+        eigs = la.eigvals(jac)
+        eigs = eigs[xp.argsort(xp.abs(eigs))]
+        return eigs[-n:]
+
     # ------------------------------------------------------------------ RG.py:244-253
     def norm_int(self, h):
         f = _f64(h.f).reshape(1, -1)

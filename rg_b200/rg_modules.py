@@ -84,6 +84,8 @@ def compute_iterates(case):
         except AttributeError as e:
             # the reference dies here on every run (quirk Q1, RG.py:237) and never reaches save_data
             print('\033[90m        eigenvalues unavailable ({}) \033[00m'.format(e))
+            if int(case.vecjl) <= 1500:   # the dense eigen-solve of the Jacobian is host work: keep it small
+                print(case.eigenvalues_batched(h_list[0], 1e-10, 5))
         save_data('iterates', data, timestr, case, info='diff     delta     lambda', display=True)
     return data
 

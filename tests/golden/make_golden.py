@@ -196,6 +196,15 @@ def main(argv):
         with ctx.Pool(NPROC, initializer=_init_worker, initargs=(over, 12345)) as pool:
             res = pool.map(_cr, list(eps), chunksize=1)
         save("surface_L5J5_n8", over=repr(over), eps=eps, data=np.array(res, dtype=np.float64).T)
+    if "surface10" in what:
+        # BASELINE config 3 at a checkable size: 6 of the 128 columns of the Nxy=128, L=J=10 critical surface
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        over = dict(L=10, J=10, CT="expm_onestep", RelDist=1e-7)
+        eps = np.linspace(0, 1, 128)[[0, 13, 40, 77, 101, 127]]
+        with ctx.Pool(NPROC, initializer=_init_worker, initargs=(over, 12345)) as pool:
+            res = pool.map(_cr, list(eps), chunksize=1)
+        save("surface_L10J10_cols", over=repr(over), eps=eps, data=np.array(res, dtype=np.float64).T)
     if "spiral" in what:
         over = dict(torus="spiral", L=6, J=6, CT="expm_multiply")
         pts = [(0.005, 0.02), (0.02, 0.1), (0.05, 0.25)]

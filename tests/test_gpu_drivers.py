@@ -94,3 +94,25 @@ def test_compute_iterates_runs(tmp_path, monkeypatch, capsys):
     assert abs(data[1][0] - 0.554) < 5e-3 and abs(data[1][1] - 3.53) < 5e-2 and abs(data[1][2] - 4.72) < 5e-2
     assert "eigenvalues unavailable" in capsys.readouterr().out
     c.close()
+
+
+def test_jacobian_columns_match_oracle():
+    """the finite-difference Jacobian behind `eigenvalues` as one batch of rg_maps.
+    dx = 1e-6 keeps the finite-difference noise (roundoff / dx) below the comparison tolerance."""
+    import rg_oracle as ro
+    c = make(L=5, J=5, CanonicalTransformation="expm_onestep")
+    orc = ro.OracleRG(ro.default_params(L=5, J=5, CT="expm_onestep"))
+    h = c.generate_1Hamiltonian([0.02, 0.02], symmetric=True)
+    h = c.rg_map(h)
+    cols = [12, 140, 300, 577]
+    dx = 1e-6
+    jac = c.jacobian(h, dx, columns=cols)
+    ho = ro.Hamiltonian(h.Omega, h.f.copy())
+    for q, col in enumerate(cols):
+        d = np.zeros(int(c.vecjl)); d[col] = dx
+        hd = ro.Hamiltonian(h.Omega, h.f + orc.sym(ro.Hamiltonian(h.Omega, d.reshape(c.r_jl))).f)
+        row = (orc.rg_map(hd).f.reshape(-1) - ho.f.reshape(-1)) / dx
+        assert np.abs(jac[q] - row).max() <= 1e-6 * max(1.0, np.abs(row).max())
+    eigs = c.eigenvalues_batched(h, 1e-6, 3)
+    assert len(eigs) == 3 and np.all(np.isfinite(eigs))
+    c.close()
