@@ -91,7 +91,8 @@ int rg_plan_create(const rg_params* params, rg_plan** out);
 int rg_plan_destroy(rg_plan* plan);
 /* geometry of the compiled schedule (for DESIGN.md / roofline arithmetic / tests) */
 int rg_plan_info(const rg_plan* plan, int32_t* threads_per_cta, int32_t* smem_bytes, int32_t* ctas_per_sm,
-                 int32_t* n_support, int64_t* fma_useful_per_liouville, int64_t* fma_executed_per_liouville);
+                 int32_t* n_support, int64_t* fma_useful_per_liouville, int64_t* fma_executed_per_liouville,
+                 int32_t* resident_ctas /* Hamiltonians in flight at once: SMs x CTAs per SM */);
 
 /* nrm_tab[k] = ||N^T Omega_k||, Omega_nu_tab[k][M] = Omega_k . nu (wrapped order), k = 0..n_tab,
    computed by the host with the reference's own calls (RG.py:210-213). */

@@ -45,7 +45,7 @@ SIGNATURES = {
     "rg_plan_create": (ctypes.c_int, [ctypes.POINTER(RGParams), ctypes.POINTER(vp)]),
     "rg_plan_destroy": (ctypes.c_int, [vp]),
     "rg_plan_info": (ctypes.c_int, [vp, c_int_p, c_int_p, c_int_p, c_int_p, ctypes.POINTER(ctypes.c_int64),
-                                    ctypes.POINTER(ctypes.c_int64)]),
+                                    ctypes.POINTER(ctypes.c_int64), c_int_p]),
     "rg_tables_create": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, ctypes.POINTER(vp)]),
     "rg_tables_destroy": (ctypes.c_int, [vp]),
     "rg_region": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, ctypes.POINTER(RGStats)]),

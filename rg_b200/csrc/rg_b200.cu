@@ -605,7 +605,7 @@ extern "C" int rg_plan_destroy(rg_plan* p) {
 }
 
 extern "C" int rg_plan_info(const rg_plan* p, int32_t* threads, int32_t* smem, int32_t* ctas_per_sm, int32_t* n_support,
-                            int64_t* fma_useful, int64_t* fma_executed) {
+                            int64_t* fma_useful, int64_t* fma_executed, int32_t* resident_ctas) {
     if (!p) return fail(-1, "null plan");
     if (threads) *threads = p->threads;
     if (smem) *smem = (int32_t)p->smem[0];
@@ -614,6 +614,7 @@ extern "C" int rg_plan_info(const rg_plan* p, int32_t* threads, int32_t* smem, i
     // the fused path runs the half-space schedule (operands are exactly symmetric after RG.sym)
     if (fma_useful) *fma_useful = p->hs[2].fma_useful;
     if (fma_executed) *fma_executed = p->hs[2].fma_executed;
+    if (resident_ctas) *resident_ctas = p->grid_max[0];
     return 0;
 }
 

@@ -247,12 +247,12 @@ class RG:
         return self._tabs[key]
 
     def plan_info(self, ct=None):
-        t, s, c, n = (ctypes.c_int32() for _ in range(4))
+        t, s, c, n, r = (ctypes.c_int32() for _ in range(5))
         fu, fe = ctypes.c_int64(), ctypes.c_int64()
         _lib.check(_lib.lib().rg_plan_info(self._plan(ct), ctypes.byref(t), ctypes.byref(s), ctypes.byref(c),
-                                            ctypes.byref(n), ctypes.byref(fu), ctypes.byref(fe)))
+                                            ctypes.byref(n), ctypes.byref(fu), ctypes.byref(fe), ctypes.byref(r)))
         return dict(threads_per_cta=t.value, smem_bytes=s.value, ctas_per_sm=c.value, n_support=n.value,
-                    fma_useful_per_liouville=fu.value, fma_executed_per_liouville=fe.value)
+                    fma_useful_per_liouville=fu.value, fma_executed_per_liouville=fe.value, resident_ctas=r.value)
 
     def _Omega_nu_flat(self):
         return _f64(xp.asarray(self.Omega_nu).reshape(-1))
@@ -476,17 +476,45 @@ class RG:
 
     # ------------------------------------------------------------------ RG.py:292-307
     def approach(self, h_list, reldist, display=False):
+        """Bisection between a converging and a diverging Hamiltonian (RG.py:292-307).
+
+        The reference evaluates one midpoint per iteration.  Here the next `depth` levels of the bisection tree
+        are evaluated speculatively in one batched launch (2^depth - 1 Hamiltonians, one CTA each): every
+        node is formed with the same `(h0 + h1) * 0.5` the sequential loop would use for it, so the path taken
+        and every array on it are bit-identical to the reference's sequence; only the untaken branches are
+        wasted.  depth 2 (3 midpoints per launch, each on a 4-CTA cluster) is the measured optimum on B200 for
+        the L=J=10 line (tools/probe_line.py: 2.34 s sequential, 1.33 s depth 2, 1.94 s depth 3 -- a launch lasts
+        as long as its slowest node, and deeper trees add nodes ever closer to the critical surface)."""
         h_list_ = copy.deepcopy(h_list)
         for h in h_list_:
             h.error = 0
+        cap = max(1, self.plan_info()["resident_ctas"])
+        depth = max(1, min(2, int(xp.log2(cap + 1))))
+        depth = int(os.environ.get("RG_B200_SPEC_DEPTH", depth))
         while self.norm_int(h_list_[0] - h_list_[1]) > reldist * self.norm(h_list_[0].f):
-            h_mid = (h_list_[0] + h_list_[1]) * 0.5
-            if self.converge(h_mid):
-                h_list_[0] = copy.deepcopy(h_mid)
-            else:
-                h_list_[1] = copy.deepcopy(h_mid)
-            if display:
-                print('\033[90m               [{:.6f}   {:.6f}] \033[00m'.format(2 * h_list_[0].f[self.ModesK[0]], 2 * h_list_[1].f[self.ModesK[0]]))
+            # tree[level] = list of (h0, h1, mid) for every interval reachable at that level
+            tree = [[(h_list_[0], h_list_[1], (h_list_[0] + h_list_[1]) * 0.5)]]
+            for _ in range(1, depth):
+                nxt = []
+                for (a, b, m) in tree[-1]:
+                    nxt.append((m, b, (m + b) * 0.5))     # taken if m converges (h0 <- m)
+                    nxt.append((a, m, (a + m) * 0.5))     # taken if m diverges  (h1 <- m)
+                tree.append(nxt)
+            flat = [node[2] for level in tree for node in level]
+            conv = self.converge_batch(flat)
+            pos, off = 0, 0
+            for level in range(depth):
+                a, b, m = tree[level][pos]
+                if level > 0 and not (self.norm_int(a - b) > reldist * self.norm(a.f)):
+                    break                                   # the sequential loop would have stopped here
+                if conv[off + pos]:
+                    h_list_[0], pos_next = copy.deepcopy(m), 2 * pos
+                else:
+                    h_list_[1], pos_next = copy.deepcopy(m), 2 * pos + 1
+                if display:
+                    print('\033[90m               [{:.6f}   {:.6f}] \033[00m'.format(2 * h_list_[0].f[self.ModesK[0]], 2 * h_list_[1].f[self.ModesK[0]]))
+                off += len(tree[level])
+                pos = pos_next
         if display:
             print('\033[96m          ε = {} \033[00m'.format([2 * h_list_[0].f[k] for k in self.K]))
         h_list_[1].error = 0
