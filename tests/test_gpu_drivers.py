@@ -61,6 +61,19 @@ def test_compute_surface_L5J5(tmp_path, monkeypatch):
     c.close()
 
 
+def test_compute_surface_L10J10_columns():
+    """BASELINE config 3 (Nxy=128, L=J=10, RelDist=1e-7) on 6 of its 128 columns, frozen from the reference
+    run through multiprocess.Pool (quirk Q2 semantics); the lock-step batched bisection must land on the
+    same critical amplitudes to RelDist."""
+    from rg_b200.rg_modules import compute_cr_batch
+    g = golden("surface_L10J10_cols")
+    c = make(L=10, J=10, CanonicalTransformation="expm_onestep", RelDist=1e-7, Nxy=128, Method="surface", SaveData=False)
+    res = np.array(compute_cr_batch([np.float64(e) for e in g["eps"]], c), dtype=np.float64).T
+    assert np.allclose(res[0], g["data"][0], rtol=0, atol=1e-15), (res[0], g["data"][0])
+    assert np.allclose(res[1], g["data"][1], rtol=4e-7, atol=0), (res[1], g["data"][1])
+    c.close()
+
+
 def test_compute_region_mat_schema(tmp_path, monkeypatch):
     """compute_region writes RG_region_<timestamp>.mat with data int64 (Nxy,Nxy,2), info (Nxy,Nxy) and every
     param_dict key except Precision (RG_modules.py:163-173)."""
