@@ -159,12 +159,14 @@ int rg_compute_m_s(rg_plan* plan, int32_t n, const double* y0, const double* y1,
    schedule in numpy.  mode: 0 = I^- support, all output modes; 1 = dense (caller-supplied y); 2 = I^-
    support, half space nu <= 0 only (exactly symmetric operands).  Arrays are malloc'ed; free with
    rg_debug_free.  A schedule has n_stages (1 or 2) stages, each a partition of the output modes into boxes
-   (stage 0 stores, stage 1 adds).  pieces: [n_stages][n_warps*4][4] = {box, begin, end, rank}, box = -1 unused.
+   (stage 0 stores, stage 1 adds).  pieces: [n_stages][n_warps*max_pieces][4] = {box, begin, end, rank}, box = -1
+   unused (max_pieces = piece slots per warp: 4, more when a warp has to own many boxes).
    cost[4] = {useful FMAs, issued FMAs (32 lanes x list cost), max per-warp list cost, total list cost}. */
 int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_t* iminus_wrapped, int32_t mode,
                       int32_t* n_warps, int32_t* n_boxes, int32_t** lane_out /*[NB*32] centred idx*/,
                       int32_t** pieces, int32_t* n_entries, uint32_t** entries /*[n*2]*/,
-                      int32_t* n_support, int32_t** supp_rec /*[M]*/, int64_t* cost, int32_t* n_stages);
+                      int32_t* n_support, int32_t** supp_rec /*[M]*/, int64_t* cost, int32_t* n_stages,
+                      int32_t* max_pieces);
 void rg_debug_free(void* p);
 
 #ifdef __cplusplus

@@ -20,6 +20,10 @@ using namespace rgdev;
 #ifndef RG_J_LIST
 #define RG_J_LIST(X) X(4) X(5) X(6) X(10)
 #endif
+// J values that also get the BIG kernel (operand records in global memory; arrays beyond one SM's shared memory)
+#ifndef RG_JBIG_LIST
+#define RG_JBIG_LIST(X) X(4) X(6)
+#endif
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -116,8 +120,8 @@ __device__ void push_neighbours(const Job& job, int item) {
     }
 }
 
-template <int J>
-__global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_kernel(const int slot, const __grid_constant__ Tables T, const __grid_constant__ Job job) {
+template <int J, bool BIG>
+__global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ? 1 : 2) rg_kernel(const int slot, const __grid_constant__ Tables T, const __grid_constant__ Job job) {
     namespace cg = cooperative_groups;
     Ctx c;
     c.slot = slot;
@@ -126,13 +130,14 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
     c.cbase = job.csize == 4 ? 6 : (job.csize == 2 ? 3 : 0);
     c.crank = job.csize > 1 ? (int)cg::this_cluster().block_rank() : 0;
     const DevPlan& P = RG_PLAN(c);
-    const Smem sm = smem_view(P, RG_SCHED(c));
-    int* sh_item = reinterpret_cast<int*>(sm.red + 64);
-    c.ws = job.ws_base + (size_t)blockIdx.x * WS_COUNT * P.vecjl;
+    int* sh_item = reinterpret_cast<int*>(smem_red() + 64);
+    c.ws = job.ws_base + (size_t)blockIdx.x * (size_t)P.ws_stride;
+    c.rec = reinterpret_cast<double2*>(c.ws + (size_t)WS_COUNT * P.vecjl);
+    const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
     c.Omega_nu = T.Omega_nu;
     // zero all records once (pads and the all-zero record stay zero for the life of the CTA)
     {
-        const int nd2 = (P.M + 1 + RG_SCHED(c).n_support) * P.rec_units;
+        const int nd2 = (P.M + 1 + (BIG ? P.M : RG_SCHED(c).n_support)) * P.rec_units;
         for (int i = threadIdx.x; i < nd2; i += blockDim.x) sm.G[i] = make_double2(0.0, 0.0);
     }
     double* fa = c.ws + (size_t)WS_FA * P.vecjl;
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
             while (P.tol_max > ni && ni > P.tol_min) {
                 if (k0 + k >= T.n_tab) { overflow = true; break; }
                 if (c.n_liou > P.max_liouville) { budget = true; break; }
-                f = rg_map_dev<J>(c, f, T, k0 + k, err, ni);
+                f = rg_map_dev<J, BIG>(c, f, T, k0 + k, err, ni);
                 ++k; ++n_maps;
                 if (job.row_len > 0 && !hot && c.n_liou > job.hot_threshold) {
                     hot = true;
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
             int err = 0; double ni;
             for (int k = 0; k < job.n_iter; ++k) {
                 if (k0 + k >= T.n_tab) { err = RG_ERR_TABLE_EXHAUSTED; break; }
-                f = rg_map_dev<J>(c, f, T, k0 + k, err, ni);
+                f = rg_map_dev<J, BIG>(c, f, T, k0 + k, err, ni);
                 ++n_maps;
             }
             __syncthreads();
@@ -221,17 +226,17 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
             const double a = job.y0[item];
             if (job.mode == 3) {
                 int err = job.err[item];
-                if (job.ct == 0) err = expm_onestep<J>(c, f, a, job.step);
-                else if (job.ct == 1) err = expm_adapt<J>(c, f, a, job.step, err);
-                else err = expm_multiply<J>(c, f, a);
+                if (job.ct == 0) err = expm_onestep<J, BIG>(c, f, a, job.step);
+                else if (job.ct == 1) err = expm_adapt<J, BIG>(c, f, a, job.step, err);
+                else err = expm_multiply<J, BIG>(c, f, a);
                 __syncthreads();
                 store_wrapped(P, f, job.f_out + (size_t)item * P.vecjl);
                 if (threadIdx.x == 0) job.err[item] = err;
             } else {
                 // RG.liouville  RG.py:115-117
                 double* dst = c.ws + (size_t)WS_T0 * P.vecjl;
-                build_Y(c, 1.0, 1.0, false);
-                liouville_apply<J>(c, f, dst, a, false);
+                build_Y<BIG>(c, 1.0, 1.0, false);
+                liouville_apply<J, BIG>(c, f, dst, a, false);
                 __syncthreads();
                 store_wrapped(P, dst, job.f_out + (size_t)item * P.vecjl);
             }
@@ -241,10 +246,10 @@ __global__ void __launch_bounds__((J >= 8) ? 384 : 256, (J >= 8) ? 1 : 2) rg_ker
             load_wrapped(P, job.y1 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y1 * P.vecjl);
             load_wrapped(P, job.y2 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y2 * P.vecjl);
             __syncthreads();
-            build_Y(c, 1.0, 1.0, false);
+            build_Y<BIG>(c, 1.0, 1.0, false);
             __syncthreads();
             int m_star; double scale, n1;
-            compute_m_s<J>(c, job.y0[item], m_star, scale, n1);
+            compute_m_s<J, BIG>(c, job.y0[item], m_star, scale, n1);
             if (threadIdx.x == 0) {
                 job.m_out[item] = m_star;
                 job.s_out[item] = scale < 2147483647.0 ? (int)scale : 2147483647;
@@ -415,9 +420,17 @@ static int dev_upload(rg_plan* p, const T* host, size_t n, T** out) {
 }
 
 typedef void (*kern_t)(const int, const Tables, const Job);
-static kern_t pick_kernel(int J) {
+static kern_t pick_kernel(int J, bool big) {
+    if (big) {
+        switch (J) {
+#define RG_CASE(j) case j: return rg_kernel<j, true>;
+            RG_JBIG_LIST(RG_CASE)
+#undef RG_CASE
+            default: return nullptr;
+        }
+    }
     switch (J) {
-#define RG_CASE(j) case j: return rg_kernel<j>;
+#define RG_CASE(j) case j: return rg_kernel<j, false>;
         RG_J_LIST(RG_CASE)
 #undef RG_CASE
         default: return nullptr;
@@ -427,22 +440,31 @@ static kern_t pick_kernel(int J) {
 // warps per CTA: one lane per output mode -> ceil(M/32) boxes; rounded up to a multiple of 4 so that the four
 // SM sub-partitions carry the same number of warps (14 warps ran 12 % slower than 16: 4+4+3+3), capped at 16
 // (512 threads x 128 registers = the whole register file).
-static int rg_warps_for(int M, int J) {
+static int rg_warps_for(int M, int J, bool big = false) {
     int w = (((M + 31) / 32 + 3) / 4) * 4;
     if (w < 4) w = 4;
-    const int wmax = (J >= 8) ? 12 : 8;   // must match __launch_bounds__ of rg_kernel<J>: 384 x 168 regs, or 256 x 128
+    const int wmax = (J >= 8 || big) ? 12 : 8;   // must match __launch_bounds__ of rg_kernel<J, BIG>: 384 x 168 regs, or 256 x 128
     if (w > wmax) w = wmax;
     const char* e = getenv("RG_B200_WARPS");
     if (e && atoi(e) >= 4 && atoi(e) <= wmax && atoi(e) % 4 == 0) w = atoi(e);
     return w;
 }
 
-static size_t smem_bytes(const rg_plan* p, int s) {
-    const rgplan::Geometry& g = p->g;
-    size_t b = (size_t)(g.M + 1 + p->hs[s].n_support) * g.rec_units * 16;
+static size_t smem_bytes(const rgplan::Geometry& g, int n_support, bool big) {
+    size_t b = big ? 0 : (size_t)(g.M + 1 + n_support) * g.rec_units * 16;
     b += (size_t)g.M * g.JP * 8;
     b += 64 * 8 + 16;
     return b;
+}
+
+// Does the Hamiltonian need the BIG kernel?  (records + out + scratch beyond the opt-in shared memory of an SM)
+static const size_t RG_SMEM_OPTIN = 232448;   // sm_100: 227 KB per CTA
+static bool needs_global_records(const rgplan::Geometry& g, const std::vector<uint16_t>& mask, size_t optin) {
+    const char* e = getenv("RG_B200_FORCE_GLOBAL");
+    if (e && atoi(e)) return true;
+    int n_support = 0;
+    for (int c = 0; c < g.M; ++c) n_support += mask[c] != 0;
+    return smem_bytes(g, n_support, false) > optin;
 }
 
 static std::vector<uint16_t> masks_from_iminus(const rgplan::Geometry& g, const uint8_t* iminus_wrapped) {
@@ -461,7 +483,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     if (prm->dim < 1 || prm->dim > 3) return fail(-2, "dim must be 1, 2 or 3");
     if (prm->J < 2 || prm->J > 15) return fail(-2, "J must be in 2..15");
     if (prm->L < 1 || prm->L > 60) return fail(-2, "L must be in 1..60");
-    if (!pick_kernel(prm->J)) return fail(-3, "no kernel compiled for J=" + std::to_string(prm->J) + " (rebuild with RG_B200_J_LIST)");
+    if (!pick_kernel(prm->J, false)) return fail(-3, "no kernel compiled for J=" + std::to_string(prm->J) + " (rebuild with RG_B200_J_LIST)");
     if (prm->ct < 0 || prm->ct > 2) return fail(-2, "unknown canonical transformation");
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -472,15 +494,21 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     p->g.init(prm->dim, prm->L, prm->J);
     const rgplan::Geometry& g = p->g;
     std::vector<uint16_t> mask = masks_from_iminus(g, prm->iminus);
-    const int n_warps = rg_warps_for(g.M, g.J);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, p->device));
+    const bool big = needs_global_records(g, mask, (size_t)prop.sharedMemPerBlockOptin);
+    if (big && !pick_kernel(prm->J, true)) {
+        delete p;
+        return fail(-3, "Hamiltonian too large for one CTA's shared memory and no global-record kernel compiled for J=" +
+                            std::to_string(prm->J) + " (rebuild with RG_JBIG_LIST)");
+    }
+    const int n_warps = rg_warps_for(g.M, g.J, big);
     for (int ci = 0; ci < 3; ++ci) {
         const int vw = n_warps << ci;   // virtual warps of a cluster of 1, 2, 4 CTAs
         p->hs[3 * ci + 0] = rgplan::make_schedule(g, mask, false, false, vw, 1 << ci);
         p->hs[3 * ci + 1] = rgplan::make_schedule(g, mask, true, false, vw, 1 << ci);
         p->hs[3 * ci + 2] = rgplan::make_schedule(g, mask, false, true, vw, 1 << ci);
     }
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, p->device));
     p->sm_count = prop.multiProcessorCount;
     p->threads = n_warps * 32;
     for (int s = 0; s < 9; ++s)
@@ -496,6 +524,8 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     dp.min_step = prm->min_step; dp.abs_tol = prm->abs_tol; dp.rel_tol = prm->rel_tol; dp.eigenvalue = prm->eigenvalue;
     dp.max_series = prm->max_series > 0 ? prm->max_series : 100000;
     dp.max_liouville = prm->max_liouville > 0 ? prm->max_liouville : 2000000LL;
+    dp.rec_global = big ? 1 : 0;
+    dp.ws_stride = (long long)WS_COUNT * g.vecjl + (big ? (long long)(2 * g.M + 1) * g.rec_units * 2 : 0LL);
     dp.debug = getenv("RG_B200_DEBUG") ? atoi(getenv("RG_B200_DEBUG")) : 0;
     // centred tables
     std::vector<double> om0(g.M), normw(g.M);
@@ -533,15 +563,16 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
         if ((rc = dev_upload(p, reinterpret_cast<const uint2*>(hs.entries.data()), hs.entries.size() / 2, &ds.entries))) return rc;
         if ((rc = dev_upload(p, hs.supp_rec.data(), hs.supp_rec.size(), &ds.supp_rec))) return rc;
         dp.sched[s].n_warps = hs.n_warps; dp.sched[s].n_support = hs.n_support;
+        dp.sched[s].maxp = hs.maxp;
         dp.sched[s].n_boxes = hs.n_boxes; dp.sched[s].half = hs.half ? 1 : 0; dp.sched[s].n_stages = hs.n_stages;
         dp.sched[s].max_rank[0] = hs.max_rank[0]; dp.sched[s].max_rank[1] = hs.max_rank[1];
         for (int r = 0; r < 4; ++r) { dp.sched[s].fin_begin[r] = hs.fin_begin[r]; dp.sched[s].fin_end[r] = hs.fin_end[r]; }
         dp.sched[s].lane_out = ds.lane_out; dp.sched[s].lane_coord = ds.lane_coord; dp.sched[s].pieces = ds.pieces;
         dp.sched[s].entries = ds.entries; dp.sched[s].supp_rec = ds.supp_rec;
     }
-    p->kernel = (void*)pick_kernel(g.J);
+    p->kernel = (void*)pick_kernel(g.J, big);
     for (int s = 0; s < 2; ++s) {
-        p->smem[s] = smem_bytes(p, s);
+        p->smem[s] = smem_bytes(g, p->hs[s].n_support, big);
         if (p->smem[s] > (size_t)prop.sharedMemPerBlockOptin) {
             if (s == 0) { rg_plan_destroy(p); return fail(-5, "Hamiltonian too large for one CTA's shared memory (" + std::to_string(p->smem[s]) + " B)"); }
             p->ctas_per_sm[s] = 0; p->grid_max[s] = 0;
@@ -577,8 +608,8 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     }
     if (getenv("RG_B200_CLUSTER")) p->cluster_pref = atoi(getenv("RG_B200_CLUSTER"));
     p->ws_ctas = (size_t)std::max(p->grid_max[0], p->grid_max[1]);
-    CU(cudaMalloc(&p->ws, p->ws_ctas * WS_COUNT * g.vecjl * sizeof(double)));
-    CU(cudaMemset(p->ws, 0, p->ws_ctas * WS_COUNT * g.vecjl * sizeof(double)));
+    CU(cudaMalloc(&p->ws, p->ws_ctas * (size_t)dp.ws_stride * sizeof(double)));
+    CU(cudaMemset(p->ws, 0, p->ws_ctas * (size_t)dp.ws_stride * sizeof(double)));
     CU(cudaMalloc(&p->ticket, sizeof(int)));
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&p->ev0));
@@ -998,17 +1029,19 @@ extern "C" int rg_compute_m_s(rg_plan* p, int32_t n, const double* y0, const dou
 // ---- host-only schedule introspection (tests replay it in numpy; no device needed)
 extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_t* iminus_wrapped, int32_t mode,
                                  int32_t* n_warps, int32_t* n_boxes, int32_t** lane_out, int32_t** pieces, int32_t* n_entries,
-                                 uint32_t** entries, int32_t* n_support, int32_t** supp_rec, int64_t* cost, int32_t* n_stages) {
+                                 uint32_t** entries, int32_t* n_support, int32_t** supp_rec, int64_t* cost, int32_t* n_stages,
+                                 int32_t* max_pieces) {
     if (dim < 1 || dim > 3 || J < 1 || J > 15 || L < 1) return fail(-2, "bad geometry");
     rgplan::Geometry g; g.init(dim, L, J);
     std::vector<uint16_t> mask = masks_from_iminus(g, iminus_wrapped);
-    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, rg_warps_for(g.M, g.J));
+    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, rg_warps_for(g.M, g.J, needs_global_records(g, mask, RG_SMEM_OPTIN)));
     if (s.n_warps < 0) return fail(-5, "too many output modes for one CTA's convolution schedule");
     *n_warps = s.n_warps; *n_boxes = s.n_boxes; *n_entries = (int)s.entries.size() / 2; *n_support = s.n_support;
     if (cost) { cost[0] = s.fma_useful; cost[1] = s.fma_executed; cost[2] = s.cost_max; cost[3] = s.cost_total; }
     *lane_out = (int32_t*)malloc(sizeof(int32_t) * s.lane_out.size());
     memcpy(*lane_out, s.lane_out.data(), sizeof(int32_t) * s.lane_out.size());
     if (n_stages) *n_stages = s.n_stages;
+    if (max_pieces) *max_pieces = s.maxp;
     *pieces = (int32_t*)malloc(sizeof(int32_t) * 4 * s.pieces.size());
     memcpy(*pieces, s.pieces.data(), sizeof(int32_t) * 4 * s.pieces.size());
     *entries = (uint32_t*)malloc(sizeof(uint32_t) * std::max<size_t>(s.entries.size(), 1));

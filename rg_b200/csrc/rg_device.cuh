@@ -12,14 +12,14 @@
 
 namespace rgdev {
 
-#define RG_MAXP 4   // pieces per warp (rgplan::MAXP)
 struct Sched {
     int n_warps, n_boxes, n_support, half, n_stages;
+    int maxp;                       // piece slots per warp and stage (rgplan::Schedule::maxp)
     int max_rank[2];                // per stage
     int fin_begin[4], fin_end[4];   // boxes owned by each CTA of a cluster
     const int* lane_out;         // [NB*32] centred mode of each lane, -1 idle
     const uint32_t* lane_coord;  // [NB*32] packed biased coords
-    const int4* pieces;          // [n_stages][NW*RG_MAXP] {box, begin, end, rank}; box = -1 unused; heads first
+    const int4* pieces;          // [n_stages][NW*maxp] {box, begin, end, rank}; box = -1 unused; heads first
     const uint2* entries;        // {packed coords of nu1, (rec<<8)|jm}
     const int* supp_rec;         // [M] record of centred mode or -1
 };
@@ -34,6 +34,8 @@ struct DevPlan {
     double min_step, abs_tol, rel_tol, eigenvalue;
     int max_series;
     long long max_liouville;   // work budget per Hamiltonian (the reference has none, quirk Q6)
+    int rec_global;            // 1: the operand records live in the CTA's global workspace (array too large for shared memory)
+    long long ws_stride;       // doubles of workspace per CTA (WS_COUNT arrays + the global records, if any)
     int debug;   // RG_B200_DEBUG experiments (0 in production): bit0 gather always hits the zero record,
                  // bit1 every entry broadcasts y record 0
     const double* omega0_nu;  // [M] centred
@@ -65,6 +67,7 @@ struct Ctx {
     int cbase;    // 3*log2(cluster size): offset of the schedule set
     int csize, crank;  // thread-block cluster size (1, 2, 4) and this CTA's rank in it
     double* ws;   // this CTA's global workspace
+    double2* rec; // global operand records (plans with rec_global), else unused
     const double* Omega_nu;  // current Omega.nu, centred, global
     long long n_liou, n_lie;
     uint64_t rng;  // state of the 1-norm estimator's +-1 columns (seeded per Hamiltonian)
@@ -72,18 +75,28 @@ struct Ctx {
     long long t_busy;         // of t_conv: clocks warp 0 spent computing its own pieces (the rest is barrier wait)
 };
 
+// Shared memory of a CTA: [red: 64 doubles of reduction scratch + 16 bytes for the work ticket | G | Y | out].
+// BIG kernels (arrays too large for one SM, e.g. n = 3 at L = J = 6: 246 KB of g records alone) keep G and Y in
+// the CTA's global workspace instead -- private to the CTA, read through L1 -- and only `red` and `out` on chip.
 struct Smem {
     double2* G;   // (M+1) records, the last one all zero
     double2* Y;   // n_support records
     double* out;  // [M][JP]
-    double* red;  // 64 doubles of reduction scratch (+ 16 bytes for the work ticket)
 };
-__device__ __forceinline__ Smem smem_view(const DevPlan& P, const Sched& S) {
+#define RG_RED_UNITS 33   // 16-byte units of the `red` block
+__device__ __forceinline__ double* smem_red() { return reinterpret_cast<double*>(smem_dyn); }
+template <bool BIG>
+__device__ __forceinline__ Smem smem_view(const DevPlan& P, const Sched& S, const Ctx& c) {
     Smem v;
-    v.G = smem_dyn;
-    v.Y = v.G + (P.M + 1) * P.rec_units;
-    v.out = reinterpret_cast<double*>(v.Y + S.n_support * P.rec_units);
-    v.red = v.out + P.M * P.JP;
+    if (BIG) {
+        v.G = c.rec;
+        v.Y = v.G + (P.M + 1) * P.rec_units;
+        v.out = reinterpret_cast<double*>(smem_dyn + RG_RED_UNITS);
+    } else {
+        v.G = smem_dyn + RG_RED_UNITS;
+        v.Y = v.G + (P.M + 1) * P.rec_units;
+        v.out = reinterpret_cast<double*>(v.Y + S.n_support * P.rec_units);
+    }
     return v;
 }
 #define RG_PLAN(c) c_plan[(c).slot]
@@ -161,8 +174,9 @@ struct LaneGeo {
     int lin;              // sum_d v_d * stride_d : centred index of (nu - nu1) = lin - index(nu1)
     unsigned lim;         // 2L
     int zero_rec;         // index of the all-zero record (M)
-    uint32_t g_base, y_base;  // shared-memory byte addresses of G and Y
+    uint32_t g_base, y_base;  // shared-memory byte addresses of G and Y (BIG: byte offsets from gb)
     int rec_bytes;
+    const char* gb;           // BIG: the CTA's global record block
 };
 
 // next entry: broadcast the list words, test nu - nu1 against the grid, form the two record addresses
@@ -178,9 +192,11 @@ __device__ __forceinline__ void decode_entry(const LaneGeo& q, const uint2& me, 
     yp = q.y_base + (uint32_t)((int)(ei >> 16) * q.rec_bytes);
 }
 
-__device__ __forceinline__ double2 lds128(uint32_t addr) {
+template <bool BIG>
+__device__ __forceinline__ double2 ldrec(const LaneGeo& q, uint32_t addr) {
     double2 v;
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    if (BIG) asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(q.gb + addr));
+    else asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
 
@@ -188,14 +204,14 @@ __device__ __forceinline__ double2 lds128(uint32_t addr) {
 // sits inside the DFMA stream (same basic block) so that its latency chain is hidden.
 // yq: window holding pairs 0..YW-1 of this entry on entry, pairs 0..YW-1 of the next entry on exit.
 // gO: Omega-half of this entry's gathered record on entry, of the next entry's on exit.
-template <int J>
+template <int J, bool BIG>
 __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
                                             double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& me, int i_next,
                                             bool more, uint32_t& gp, uint32_t& yp, int& jm) {
     typedef RecGeom<J> R;
     double gD[2 * R::ND2];
 #pragma unroll
-    for (int u = 0; u < R::ND2; ++u) { const double2 t = lds128(gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
+    for (int u = 0; u < R::ND2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
     uint32_t gp_n = gp, yp_n = yp;
     int jm_n = jm;
 #pragma unroll
@@ -203,8 +219,8 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
         const double2 t = yq[k % R::YW];
         if (k == 1) decode_entry(q, me, i_next & 31, gp_n, yp_n, jm_n);   // after the first block has issued; past the
                                                                         // chunk end this reads a valid dummy entry
-        if (k + R::YW < R::NPAD) yq[k % R::YW] = lds128(yp + 16 * R::unit(k + R::YW));
-        else yq[k % R::YW] = lds128(yp_n + 16 * R::unit(k + R::YW - R::NPAD));
+        if (k + R::YW < R::NPAD) yq[k % R::YW] = ldrec<BIG>(q, yp + 16 * R::unit(k + R::YW));
+        else yq[k % R::YW] = ldrec<BIG>(q, yp_n + 16 * R::unit(k + R::YW - R::NPAD));
         if (k >= R::NP) continue;   // padding pair
         if (k < R::NP1) {
             // conv(dA y, Omega g): y1[j1] times B1[j2] = gO[j2]
@@ -217,7 +233,7 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
             }
             if (k == R::NP1 - 1) {   // next entry's Omega-half lands while the d-half is consumed
 #pragma unroll
-                for (int u = 0; u < R::NO2; ++u) { const double2 g2 = lds128(gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
+                for (int u = 0; u < R::NO2; ++u) { const double2 g2 = ldrec<BIG>(q, gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
             }
         } else {
             // conv(Omega y, dA g): y2[j1] times B2[j2] = gD[j2], j2 < J ; subtracted
@@ -236,7 +252,7 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
 // One list entry with only the first jm Taylor levels of y present (or, jm = J+2, a caller-supplied generator):
 // blocks run in ascending j1 and stop at the first absent level; y values are read on demand.  Keeps the
 // hand-over protocol of taylor_full (window and gO hold the next entry's data on exit).
-template <int J>
+template <int J, bool BIG>
 __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
                                                double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& me, int i_next,
                                                bool more, uint32_t& gp, uint32_t& yp, int& jm) {
@@ -244,7 +260,7 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     constexpr int JP = J + 1;
     double gD[2 * R::ND2];
 #pragma unroll
-    for (int u = 0; u < R::ND2; ++u) { const double2 t = lds128(gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
+    for (int u = 0; u < R::ND2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
     uint32_t gp_n = gp, yp_n = yp;
     int jm_n = jm;
     decode_entry(q, me, i_next & 31, gp_n, yp_n, jm_n);
@@ -253,7 +269,7 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     for (int k = 0; k < R::NP1; ++k) {
         const int j1 = 2 * k;
         if (!(j1 + 1 < jm)) break;
-        const double2 t = (k < R::YW) ? yq[k] : lds128(yp + 16 * R::unit(k));
+        const double2 t = (k < R::YW) ? yq[k] : ldrec<BIG>(q, yp + 16 * R::unit(k));
 #pragma unroll
         for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, gO[j2], acc[j1 + j2]);
         if (j1 + 1 < J && j1 + 2 < jm) {
@@ -263,17 +279,18 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     }
     if (JP < jm) {  // caller-supplied y with y1[J] != 0 (never on the fused path)
         double a;
-        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(yp + 8 * R::IDXJ));
+        if (BIG) asm volatile("ld.global.f64 %0, [%1];" : "=d"(a) : "l"(q.gb + yp + 8 * R::IDXJ));
+        else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(yp + 8 * R::IDXJ));
         acc[J] = fma(a, gO[0], acc[J]);
     }
 #pragma unroll
-    for (int u = 0; u < R::NO2; ++u) { const double2 g2 = lds128(gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
+    for (int u = 0; u < R::NO2; ++u) { const double2 g2 = ldrec<BIG>(q, gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
     // conv(Omega y, dA g): y2[j1] non-zero iff j1 < jm ; subtracted
 #pragma unroll
     for (int k = 0; k < R::NP2; ++k) {
         const int j1 = 2 * k;
         if (!(j1 < jm)) break;
-        const double2 t = (R::NP1 + k < R::YW) ? yq[R::NP1 + k] : lds128(yp + 16 * R::unit(R::NP1 + k));
+        const double2 t = (R::NP1 + k < R::YW) ? yq[R::NP1 + k] : ldrec<BIG>(q, yp + 16 * R::unit(R::NP1 + k));
 #pragma unroll
         for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, gD[j2], acc[j1 + j2]);
         if (j1 + 1 <= J && j1 + 1 < jm) {
@@ -282,16 +299,16 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
         }
     }
 #pragma unroll
-    for (int k = 0; k < R::YW; ++k) yq[k] = lds128(yp_n + 16 * R::unit(k));
+    for (int k = 0; k < R::YW; ++k) yq[k] = ldrec<BIG>(q, yp_n + 16 * R::unit(k));
     gp = gp_n; yp = yp_n; jm = jm_n;
 }
 
-template <int J>
+template <int J, bool BIG>
 __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, int e_end, double (&acc)[J + 1]) {
     typedef RecGeom<J> R;
     const DevPlan& P = RG_PLAN(c);
     const Sched& S = RG_SCHED(c);
-    const Smem sm = smem_view(P, S);
+    const Smem sm = smem_view<BIG>(P, S, c);
     const uint2* const entries = S.entries;
     const int lane = threadIdx.x & 31;
     const uint32_t mc = S.lane_coord[box * 32 + lane];
@@ -300,9 +317,16 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     q.lin = q.v0 * P.stride0 + q.v1 * P.stride1 + q.v2 * P.stride2;
     q.lim = 2u * (unsigned)P.L;
     q.zero_rec = P.M;
-    q.g_base = (uint32_t)__cvta_generic_to_shared(sm.G);
-    q.y_base = (uint32_t)__cvta_generic_to_shared(sm.Y);
     q.rec_bytes = P.rec_units * 16;
+    if (BIG) {
+        q.gb = reinterpret_cast<const char*>(sm.G);
+        q.g_base = 0u;
+        q.y_base = (uint32_t)((P.M + 1) * q.rec_bytes);
+    } else {
+        q.gb = nullptr;
+        q.g_base = (uint32_t)__cvta_generic_to_shared(sm.G);
+        q.y_base = (uint32_t)__cvta_generic_to_shared(sm.Y);
+    }
     double gO[2 * R::NO2];
     double2 yq[R::YW];
 #pragma unroll
@@ -315,21 +339,21 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
         int jm;
         decode_entry(q, me, 0, gp, yp, jm);
 #pragma unroll
-        for (int u = 0; u < R::NO2; ++u) { const double2 t = lds128(gp + 16 * (R::ND2 + u)); gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
+        for (int u = 0; u < R::NO2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * (R::ND2 + u)); gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
 #pragma unroll
-        for (int k = 0; k < R::YW; ++k) yq[k] = lds128(yp + 16 * R::unit(k));
+        for (int k = 0; k < R::YW; ++k) yq[k] = ldrec<BIG>(q, yp + 16 * R::unit(k));
 #pragma unroll 1
         for (int i = 0; i < cnt; ++i) {
             // the last entry of a chunk prefetches from its own records (harmless, keeps the loop uniform)
             const bool more = (i + 1 < cnt);
-            if (jm == J + 1) taylor_full<J>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
-            else taylor_partial<J>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            if (jm == J + 1) taylor_full<J, BIG>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            else taylor_partial<J, BIG>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
         }
     }
 }
 
 // out[nu][j] = conv(dA y, Omega g) - conv(Omega y, dA g)  (G, Y in shared memory).  Ends with a barrier.
-// Every warp owns up to RG_MAXP pieces of the boxes' source lists: heads (rank 0) are stored as they
+// Every warp owns up to S.maxp pieces of the boxes' source lists: heads (rank 0) are stored as they
 // finish, the single continuation a warp may hold (rank r > 0) is added in phase r -- a fixed order, so
 // the result does not depend on timing.  On the half-space schedule only modes nu <= 0 are produced.
 //
@@ -338,12 +362,12 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
 // each CTA a contiguous group of whole boxes, CTA r computes them exactly as above with its own warps
 // (virtual warps [r*W, (r+1)*W)) and then broadcasts the finished rows into the `out` buffer of every peer
 // through distributed shared memory: two cluster barriers and (csize-1) x its share of `out` per term.
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ void conv_all(Ctx& c) {
     constexpr int JP = J + 1;
     namespace cg = cooperative_groups;
     const Sched& S = RG_SCHED(c);
-    double* const out = smem_view(RG_PLAN(c), S).out;
+    double* const out = smem_view<BIG>(RG_PLAN(c), S, c).out;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, nwc = (int)(blockDim.x >> 5);
     const int vw = c.crank * nwc + w;
     const long long t_begin = clock64();
@@ -352,16 +376,16 @@ __device__ __noinline__ void conv_all(Ctx& c) {
     // stage 0 stores its sums; stage 1 (another partition of the output modes, the remaining source modes)
     // adds on top once stage 0 is complete
     for (int st = 0; st < S.n_stages; ++st) {
-        const int4* pieces = S.pieces + (size_t)st * S.n_warps * RG_MAXP;
+        const int4* pieces = S.pieces + (size_t)st * S.n_warps * S.maxp;
         int4 held = make_int4(-1, 0, 0, 0);
         const long long t_stage = clock64();
         if (vw < S.n_warps) {
 #pragma unroll 1
-            for (int q = 0; q < RG_MAXP; ++q) {
-                const int4 p = pieces[vw * RG_MAXP + q];
+            for (int q = 0; q < S.maxp; ++q) {
+                const int4 p = pieces[vw * S.maxp + q];
                 if (p.x < 0) continue;
                 if (p.w > 0) { held = p; continue; }
-                conv_piece<J>(c, p.x, p.y, p.z, acc);
+                conv_piece<J, BIG>(c, p.x, p.y, p.z, acc);
                 const int nu = S.lane_out[p.x * 32 + lane];
                 if (nu >= 0) {
                     if (st == 0) {
@@ -373,7 +397,7 @@ __device__ __noinline__ void conv_all(Ctx& c) {
                     }
                 }
             }
-            if (held.x >= 0) conv_piece<J>(c, held.x, held.y, held.z, acc);
+            if (held.x >= 0) conv_piece<J, BIG>(c, held.x, held.y, held.z, acc);
         }
         c.t_busy += clock64() - t_stage;
         __syncthreads();
@@ -411,10 +435,11 @@ __device__ __noinline__ void conv_all(Ctx& c) {
 
 // ------------------------------------------------------------------------------------------------
 // records of g: d-type = dA g (RG.py:76 roll(f*J_,-1)), Omega-type = Omega_nu*g.  src: global [j][nu].
+template <bool BIG>
 __device__ __noinline__ void build_G(const Ctx& c, const double* __restrict__ src) {
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M, J = P.J;
-    const Smem sm = smem_view(P, RG_SCHED(c));
+    const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
         double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
         const double om = c.Omega_nu[nu];
@@ -427,13 +452,14 @@ __device__ __noinline__ void build_G(const Ctx& c, const double* __restrict__ sr
 }
 
 // records of y scaled by `step` (item*step, RG.py:176) or divided by `scale` (item/scale, RG.py:156)
+template <bool BIG>
 __device__ __noinline__ void build_Y(const Ctx& c, double step, double divisor, bool use_div) {
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M, J = P.J;
     const double* y1 = c.ws + (size_t)WS_Y1 * P.vecjl;
     const double* y2 = c.ws + (size_t)WS_Y2 * P.vecjl;
     const Sched& S = RG_SCHED(c);
-    const Smem sm = smem_view(P, S);
+    const Smem sm = smem_view<BIG>(P, S, c);
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
         const int rec = S.supp_rec[nu];
         if (rec < 0) continue;
@@ -451,7 +477,7 @@ __device__ __noinline__ void build_Y(const Ctx& c, double step, double divisor, 
 // One series term: sh = [y3 +] (a0*dA g + conv) [/ m]; f += sh; G <- records of sh.
 // Returns (norm(sh), norm(f)).  Thread <-> mode nu.  On the half-space schedule the thread of nu <= 0 also
 // writes the mirror mode -nu (sh, f are exactly symmetric, Omega_nu exactly antisymmetric).
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ double2 series_epilogue(Ctx& c, double* __restrict__ f, double a0, bool first, double y3mul,
                                                 double y3div, bool use_div, double m) {
     constexpr int JP = J + 1;
@@ -460,7 +486,7 @@ __device__ __noinline__ double2 series_epilogue(Ctx& c, double* __restrict__ f, 
     const bool half = RG_SCHED(c).half != 0;
     const int nmax = half ? (M + 1) / 2 : M;
     const double* y3 = c.ws + (size_t)WS_Y3 * P.vecjl;
-    const Smem sm = smem_view(P, RG_SCHED(c));
+    const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
     const long long t_begin = clock64();
     double ps = 0.0, pf = 0.0;
     for (int nu = threadIdx.x; nu < nmax; nu += blockDim.x) {
@@ -506,7 +532,7 @@ __device__ __noinline__ double2 series_epilogue(Ctx& c, double* __restrict__ f, 
             }
         }
     }
-    const double2 res = block_reduce2(sm.red, type, ps, pf);
+    const double2 res = block_reduce2(smem_red(), type, ps, pf);
     c.t_epi += clock64() - t_begin;
     return res;
 }
@@ -517,7 +543,7 @@ __device__ __noinline__ void copy_arr(const Ctx& c, double* dst, const double* s
 }
 
 // RG.expm_onestep (RG.py:173-192) in place on f (global).  y in WS_Y1..3, a_unscaled = y[0].
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, double step, double divisor, bool use_div, int m_star) {
     const DevPlan& P = RG_PLAN(c);
     const double tol = 1.1102230246251565e-16;
@@ -525,15 +551,15 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
     int err = 0;
     const int sidx_saved = c.sidx;
     if (c.sidx == 0 && c.symm) c.sidx = 2;   // exactly symmetric f and antisymmetric y: compute nu <= 0 only
-    build_Y(c, step, divisor, use_div);
-    build_G(c, f);
+    build_Y<BIG>(c, step, divisor, use_div);
+    build_G<BIG>(c, f);
     __syncthreads();
-    conv_all<J>(c);
-    double2 r = series_epilogue<J>(c, f, a0, true, step, divisor, use_div, 1.0);
+    conv_all<J, BIG>(c);
+    double2 r = series_epilogue<J, BIG>(c, f, a0, true, step, divisor, use_div, 1.0);
     double c1 = r.x;
     for (int m = 2; m_star <= 0 || m <= m_star; ++m) {
-        conv_all<J>(c);
-        r = series_epilogue<J>(c, f, a0, false, 0.0, 1.0, false, (double)m);
+        conv_all<J, BIG>(c);
+        r = series_epilogue<J, BIG>(c, f, a0, false, 0.0, 1.0, false, (double)m);
         const double c2 = r.x;
         if (c1 + c2 < tol * r.y) break;
         else if (c1 + c2 > P.tol_max) { err = 1; break; }
@@ -544,9 +570,9 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
     return err;
 }
 
-template <int J>
+template <int J, bool BIG>
 __device__ __forceinline__ int expm_onestep(Ctx& c, double* f, double a_unscaled, double step) {
-    return expm_series<J>(c, f, a_unscaled, step, 1.0, false, 0);
+    return expm_series<J, BIG>(c, f, a_unscaled, step, 1.0, false, 0);
 }
 
 // norm(h1 - h2), norm(h1)
@@ -562,11 +588,11 @@ __device__ __noinline__ double2 diff_norms(const Ctx& c, const double* h1, const
             norm_acc(type, p1, a, w);
         }
     }
-    return block_reduce2(smem_view(P, RG_SCHED(c)).red, type, pd, p1);
+    return block_reduce2(smem_red(), type, pd, p1);
 }
 
 // RG.expm_adapt (RG.py:194-205): the recursion unrolled into a depth-first stack of sub-steps.
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ int expm_adapt(Ctx& c, double* f, double a_unscaled, double step0, int err_in) {
     const DevPlan& P = RG_PLAN(c);
     double* h1 = c.ws + (size_t)WS_H1 * P.vecjl;
@@ -577,18 +603,18 @@ __device__ __noinline__ int expm_adapt(Ctx& c, double* f, double a_unscaled, dou
     while (sp > 0) {
         const double s = stack[--sp];
         if (s < P.min_step || sp >= 60) {  // RG.py:196-198 (error=4 is dead, quirk Q3)
-            err = expm_onestep<J>(c, f, a_unscaled, s);
+            err = expm_onestep<J, BIG>(c, f, a_unscaled, s);
             __syncthreads();
             continue;
         }
         copy_arr(c, h1, f);
         copy_arr(c, h2, f);
         __syncthreads();
-        expm_onestep<J>(c, h1, a_unscaled, s);
+        expm_onestep<J, BIG>(c, h1, a_unscaled, s);
         __syncthreads();
-        expm_onestep<J>(c, h2, a_unscaled, 0.5 * s);
+        expm_onestep<J, BIG>(c, h2, a_unscaled, 0.5 * s);
         __syncthreads();
-        expm_onestep<J>(c, h2, a_unscaled, 0.5 * s);
+        expm_onestep<J, BIG>(c, h2, a_unscaled, 0.5 * s);
         __syncthreads();
         const double2 r = diff_norms(c, h1, h2);
         if (r.x < P.abs_tol + P.rel_tol * r.y) {
@@ -659,7 +685,7 @@ __device__ __noinline__ double2 sym_and_norms(Ctx& c, double* f, bool do_sym) {
         }
     }
     c.symm = __syncthreads_or(asym) ? 0 : 1;
-    return block_reduce2(smem_view(P, RG_SCHED(c)).red, type, pim, pint);
+    return block_reduce2(smem_red(), type, pim, pint);
 }
 
 // head of RG.rg_map (RG.py:210-216): dst = ren[j] * src[j][sign*N*nu] on the mask, else 0
@@ -668,7 +694,7 @@ __device__ __noinline__ void reindex_rescale(const Ctx& c, const double* __restr
     const int M = P.M, J = P.J, c0 = (M - 1) / 2;
     const double f2 = src[2 * M + c0];
     const double base = 2 * nrm / P.eigenvalue * f2;
-    double* red = smem_view(P, RG_SCHED(c)).red;
+    double* red = smem_red();
     if (threadIdx.x <= J) red[threadIdx.x] = pow(base, (double)(2 - (int)threadIdx.x)) / (2 * f2);
     __syncthreads();
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
@@ -684,10 +710,10 @@ struct Tables {
     const double* Omega_nu;  // [(n_tab+1)][M] centred
 };
 
-template <int J> __device__ int expm_multiply(Ctx& c, double* f, double a_unscaled);  // rg_multiply.cuh
+template <int J, bool BIG> __device__ int expm_multiply(Ctx& c, double* f, double a_unscaled);  // rg_multiply.cuh
 
 // RG.rg_map (RG.py:207-228).  f points to the current array (WS_FA or WS_FB); returns the new current.
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, int k, int& err_out, double& norm_int_out) {
     const DevPlan& P = RG_PLAN(c);
     double* fa = c.ws + (size_t)WS_FA * P.vecjl;
@@ -701,9 +727,9 @@ __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, i
     while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie && c.n_liou <= P.max_liouville) {
         const double a = generate_y(c, f);
         __syncthreads();
-        if (P.ct == 0) err = expm_onestep<J>(c, f, a, 1.0);
-        else if (P.ct == 1) err = expm_adapt<J>(c, f, a, 1.0, err);
-        else err = expm_multiply<J>(c, f, a);
+        if (P.ct == 0) err = expm_onestep<J, BIG>(c, f, a, 1.0);
+        else if (P.ct == 1) err = expm_adapt<J, BIG>(c, f, a, 1.0, err);
+        else err = expm_multiply<J, BIG>(c, f, a);
         __syncthreads();
         nn = sym_and_norms(c, f, true);
         ++kl;

@@ -12,15 +12,15 @@ namespace rgdev {
 
 // dst = L_y src = a0*dA src + conv(dA y, Omega src) - conv(Omega y, dA src)   (RG.py:115-117)
 // Y records must already hold y (build_Y).  src, dst: global [j][nu]; dst may alias src.
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ void liouville_apply(Ctx& c, const double* src, double* dst, double a0, bool negate) {
     constexpr int JP = J + 1;
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M;
-    const Smem sm = smem_view(P, RG_SCHED(c));
-    build_G(c, src);
+    const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
+    build_G<BIG>(c, src);
     __syncthreads();
-    conv_all<J>(c);
+    conv_all<J, BIG>(c);
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
         const double* r = reinterpret_cast<const double*>(sm.G + nu * P.rec_units);
 #pragma unroll
@@ -52,19 +52,19 @@ __device__ __noinline__ double2 abs_sums(const Ctx& c, const double* a, const do
     const DevPlan& P = RG_PLAN(c);
     double pa = 0.0, pb = 0.0;
     for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) { pa += fabs(a[i]); pb += fabs(b[i]); }
-    return block_reduce2(smem_view(P, RG_SCHED(c)).red, 0, pa, pb);
+    return block_reduce2(smem_red(), 0, pa, pb);
 }
 // (a.b, a.d)
 __device__ __noinline__ double2 dots(const Ctx& c, const double* a, const double* b, const double* d) {
     const DevPlan& P = RG_PLAN(c);
     double pa = 0.0, pb = 0.0;
     for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) { const double v = a[i]; pa += v * b[i]; pb += v * d[i]; }
-    return block_reduce2(smem_view(P, RG_SCHED(c)).red, 0, pa, pb);
+    return block_reduce2(smem_red(), 0, pa, pb);
 }
 // arg max of h over indices not in excl[0..n_excl): larger value first, ties -> larger index
 __device__ __noinline__ int block_argmax(const Ctx& c, const double* h, const int* excl, int n_excl, double* vmax) {
     const DevPlan& P = RG_PLAN(c);
-    double* red = smem_view(P, RG_SCHED(c)).red;
+    double* red = smem_red();
     double bv = -1.0; int bi = -1;
     for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
         bool skip = false;
@@ -92,10 +92,10 @@ __device__ __noinline__ int block_argmax(const Ctx& c, const double* h, const in
 }
 
 // out = (L_y)^p x  or, for the "adjoint" the reference hands to scipy, (-L_y)^p x
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ void apply_pow(Ctx& c, const double* x, double* out, double a0, int p, bool adj) {
-    liouville_apply<J>(c, x, out, a0, adj);
-    for (int k = 1; k < p; ++k) liouville_apply<J>(c, out, out, a0, adj);
+    liouville_apply<J, BIG>(c, x, out, a0, adj);
+    for (int k = 1; k < p; ++k) liouville_apply<J, BIG>(c, out, out, a0, adj);
 }
 
 __device__ __forceinline__ bool isin(int v, const int* set, int n) {
@@ -105,7 +105,7 @@ __device__ __forceinline__ bool isin(int v, const int* set, int n) {
 }
 
 // onenormest(A**p) with A = L_y (Y records must hold the unscaled y).  Returns the estimate of ||A^p||_1.
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ double onenormest_pow(Ctx& c, double a0, int p) {
     const DevPlan& P = RG_PLAN(c);
     const int n = P.vecjl, t = 2, itmax = 5;
@@ -124,8 +124,8 @@ __device__ __noinline__ double onenormest_pow(Ctx& c, double a0, int p) {
     double est_old = 0.0, est = 0.0;
     int k = 1;
     for (;;) {
-        apply_pow<J>(c, X[0], Yc[0], a0, p, false);
-        apply_pow<J>(c, X[1], Yc[1], a0, p, false);
+        apply_pow<J, BIG>(c, X[0], Yc[0], a0, p, false);
+        apply_pow<J, BIG>(c, X[1], Yc[1], a0, p, false);
         const double2 mags = abs_sums(c, Yc[0], Yc[1]);
         const int best_j = (mags.y > mags.x) ? 1 : 0;
         est = best_j ? mags.y : mags.x;
@@ -157,8 +157,8 @@ __device__ __noinline__ double onenormest_pow(Ctx& c, double a0, int p) {
             d1 = dots(c, S[1], So[0], So[1]);
         }
         // (3) Z = A^H S ; h = max_j |Z_ij|
-        apply_pow<J>(c, S[0], Yc[0], a0, p, true);
-        apply_pow<J>(c, S[1], Yc[1], a0, p, true);
+        apply_pow<J, BIG>(c, S[0], Yc[0], a0, p, true);
+        apply_pow<J, BIG>(c, S[1], Yc[1], a0, p, true);
         for (int i = threadIdx.x; i < n; i += blockDim.x) H[i] = fmax(fabs(Yc[0][i]), fabs(Yc[1][i]));
         __syncthreads();
         // (4)
@@ -200,14 +200,14 @@ __device__ __forceinline__ int compute_p_max(int m_max) {   // RG.py:125-128
 }
 
 // RG.compute_m_s (RG.py:130-150), n0 = 1, ell = 2.  Y records must hold the unscaled y.
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ void compute_m_s(Ctx& c, double a0, int& m_out, double& s_out, double& norm1_out) {
     const DevPlan& P = RG_PLAN(c);
     const int m_max = P.n_theta;
     const double n0 = 1.0, ell = 2.0;
     bool have = false;
     double best_m = 0.0, best_s = 0.0;
-    const double norm_ls = onenormest_pow<J>(c, a0, 1);
+    const double norm_ls = onenormest_pow<J, BIG>(c, a0, 1);
     norm1_out = norm_ls;
     const int p_max = compute_p_max(m_max);
     if (norm_ls < 2 * ell * p_max * (p_max + 3) * P.theta[m_max - 1] / (n0 * m_max)) {
@@ -218,7 +218,7 @@ __device__ __noinline__ void compute_m_s(Ctx& c, double a0, int& m_out, double& 
     } else {
         double norm_d[16];
         const int nd = p_max < 16 ? p_max : 16;
-        for (int p = 2; p <= nd + 1; ++p) norm_d[p - 2] = pow(onenormest_pow<J>(c, a0, p), 1.0 / (double)p);
+        for (int p = 2; p <= nd + 1; ++p) norm_d[p - 2] = pow(onenormest_pow<J, BIG>(c, a0, p), 1.0 / (double)p);
         for (int p = 2; p <= nd; ++p) {
             const double a = norm_d[p - 2], b = norm_d[(p - 1) % nd];
             const double alpha = a > b ? a : b;
@@ -235,17 +235,17 @@ __device__ __noinline__ void compute_m_s(Ctx& c, double a0, int& m_out, double& 
 }
 
 // RG.expm_multiply (RG.py:152-171) in place on f.
-template <int J>
+template <int J, bool BIG>
 __device__ __noinline__ int expm_multiply(Ctx& c, double* f, double a_unscaled) {
     int m_star; double scale, n1;
-    build_Y(c, 1.0, 1.0, false);
+    build_Y<BIG>(c, 1.0, 1.0, false);
     __syncthreads();
-    compute_m_s<J>(c, a_unscaled, m_star, scale, n1);
+    compute_m_s<J, BIG>(c, a_unscaled, m_star, scale, n1);
     int err = 0;
     // a non-finite or absurd scale would never terminate in the reference either (range(scale)); cap it
     const long long reps = (scale < 1e9) ? (long long)scale : 1000000000LL;
     for (long long r = 0; r < reps && c.n_liou <= RG_PLAN(c).max_liouville; ++r) {
-        const int e = expm_series<J>(c, f, a_unscaled, 1.0, scale, true, m_star);
+        const int e = expm_series<J, BIG>(c, f, a_unscaled, 1.0, scale, true, m_star);
         if (e) err = 1;
         __syncthreads();
     }

@@ -63,7 +63,7 @@ inline int taylor_fma(int jm, int J) {
 
 struct Piece { int box, begin, end, rank; };  // rank: position of the piece within its box's list (0 = head)
 
-constexpr int MAXP = 4;    // pieces per warp and stage: any number of heads (rank 0) up to MAXP-1, at most one continuation
+constexpr int MAXP = 4;    // least number of piece slots per warp and stage: any number of heads (rank 0), at most one continuation
 constexpr int MAXSTAGE = 2;
 
 // A schedule has one or two STAGES.  A stage is a partition of the output modes into boxes of 32 lanes plus,
@@ -75,6 +75,7 @@ struct Schedule {
     int n_warps = 0;    // warps of the cluster (csize CTAs x warps per CTA); pieces are dealt to these
     int csize = 1;      // CTAs per Hamiltonian
     int n_stages = 1;
+    int maxp = MAXP;    // piece slots per warp and stage (grows with the number of boxes a warp has to own)
     int fin_begin[4] = {0, 0, 0, 0}, fin_end[4] = {0, 0, 0, 0};   // boxes owned (computed and broadcast) by each CTA (1 stage only)
     int n_boxes = 0;    // boxes of all stages
     int n_support = 0;
@@ -82,7 +83,7 @@ struct Schedule {
     bool half = false;  // outputs restricted to the half space nu <= 0 (exactly symmetric operands)
     std::vector<int32_t> lane_out;     // [NB*32] centred mode index or -1
     std::vector<uint32_t> lane_coord;  // [NB*32] packed biased coords (0xFFFFFFFF idle)
-    std::vector<Piece> pieces;         // [n_stages][NW*MAXP], box = -1 for unused slots; heads first, continuation last
+    std::vector<Piece> pieces;         // [n_stages][NW*maxp], box = -1 for unused slots; heads first, continuation last
     std::vector<uint32_t> entries;     // [n*2]: {biased coords of nu1 (8 bits each) | jm<<24, centred index | rec<<16}
     std::vector<int32_t> supp_rec;     // [M] record index of centred nu1, -1 if not in support
     std::vector<uint8_t> jm;           // [M] 1 + highest I^- level (0 = not in support)
@@ -169,9 +170,11 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
     s.n_boxes = NBS * s.n_stages;
     s.n_warps = n_warps > 0 ? n_warps : NBS;
     const int NW = s.n_warps, NWc = NW / csize;
+    s.maxp = std::max(MAXP, (NBS + NWc - 1) / NWc + 2);
+    const int MP = s.maxp;
     s.lane_out.assign(s.n_boxes * 32, -1);
     s.lane_coord.assign(s.n_boxes * 32, 0xFFFFFFFFu);
-    s.pieces.assign((size_t)s.n_stages * NW * MAXP, Piece{-1, 0, 0, 0});
+    s.pieces.assign((size_t)s.n_stages * NW * MP, Piece{-1, 0, 0, 0});
     std::vector<int64_t> wcost(NW, 0);
     for (int st = 0; st < s.n_stages; ++st) {
         const std::vector<int>& order = orders[st];
@@ -224,7 +227,7 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
         for (int r = 0; r < 4; ++r) { s.fin_begin[r] = r < csize ? box0 + gbeg[r] : box0 + NBS; s.fin_end[r] = r < csize ? box0 + gbeg[r + 1] : box0 + NBS; }
         // ---- inside every CTA: deal the concatenated lists of its boxes to its warps in equal-cost segments.  A
         // warp's segment starts with at most one continuation of a box (rank > 0) followed by heads of later boxes.
-        Piece* pieces = s.pieces.data() + (size_t)st * NW * MAXP;
+        Piece* pieces = s.pieces.data() + (size_t)st * NW * MP;
         std::vector<int> npieces(NW, 0);
         for (int r = 0; r < csize; ++r) {
             int64_t gtotal = 0;
@@ -238,7 +241,7 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
                 size_t k = 0;
                 do {
                     // open a piece of box b on warp w
-                    while (w < w1 - 1 && (npieces[w] >= MAXP || (rank > 0 && npieces[w] > 0) ||
+                    while (w < w1 - 1 && (npieces[w] >= MP || (rank > 0 && npieces[w] > 0) ||
                                           acc * NWc >= gtotal * (int64_t)(w - w0 + 1))) ++w;
                     Piece pc{box0 + b, (int)s.entries.size() / 2, 0, rank};
                     while (k < lists[b].size()) {
@@ -252,14 +255,14 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
                         ++k;
                     }
                     pc.end = (int)s.entries.size() / 2;
-                    if (npieces[w] >= MAXP) { s.n_warps = -1; return s; }   // too many boxes for this CTA; reported by the caller
+                    if (npieces[w] >= MP) { s.n_warps = -1; return s; }   // too many boxes for this CTA; reported by the caller
                     // heads first, the continuation (if any) last
                     if (rank == 0) {
                         int q = npieces[w];
-                        if (q > 0 && pieces[w * MAXP + q - 1].rank > 0) { pieces[w * MAXP + q] = pieces[w * MAXP + q - 1]; pieces[w * MAXP + q - 1] = pc; }
-                        else pieces[w * MAXP + q] = pc;
+                        if (q > 0 && pieces[w * MP + q - 1].rank > 0) { pieces[w * MP + q] = pieces[w * MP + q - 1]; pieces[w * MP + q - 1] = pc; }
+                        else pieces[w * MP + q] = pc;
                     } else {
-                        pieces[w * MAXP + npieces[w]] = pc;
+                        pieces[w * MP + npieces[w]] = pc;
                     }
                     ++npieces[w];
                     s.max_rank[st] = std::max(s.max_rank[st], rank);

@@ -213,6 +213,13 @@ def main(argv):
         over = dict(torus="spiral", L=4, J=4, CT="expm_onestep")
         region_fixture("region_spiral_L4J4_6x6_expm_onestep", over,
                        np.linspace(0, 0.05, 6), np.linspace(0, 0.25, 6))
+    if "spiral6" in what:
+        # BASELINE config 5 at a checkable size: the 4x4 strided sub-grid (ix, iy in {16, 48, 80, 112}) of the
+        # Nxy=128 spiral-mean region, L=J=6 -- about 30-150 s per point and core in the reference
+        full_x, full_y = np.linspace(0, 0.05, 128), np.linspace(0, 0.25, 128)
+        for ct in ("expm_onestep", "expm_multiply"):
+            over = dict(torus="spiral", L=6, J=6, CT=ct)
+            region_fixture("region_spiral_L6J6_sub4_" + ct, over, full_x[16::32], full_y[16::32])
     print("done in %.1fs" % (time.time() - t00))
 
 

@@ -79,22 +79,20 @@ def test_product_never_touches_the_oracle():
 
 
 # ------------------------------------------------------------------------------------------ schedule replay
-MAXP = 4
-
-
 def fetch_schedule(c, mode):
     """mode: 0 sparse (I^- support), 1 dense, 2 sparse half-space."""
     L_ = _lib.lib()
-    nw, nb, ne, ns, nst = (ctypes.c_int32() for _ in range(5))
+    nw, nb, ne, ns, nst, mp = (ctypes.c_int32() for _ in range(6))
     lane_out, pieces, supp = (ctypes.POINTER(ctypes.c_int32)() for _ in range(3))
     entries = ctypes.POINTER(ctypes.c_uint32)()
     cost = (ctypes.c_int64 * 4)()
     im = np.ascontiguousarray(c.Iminus.reshape(-1), dtype=np.uint8)
     _lib.check(L_.rg_debug_schedule(c.dim, c.L, c.J, im.ctypes.data, int(mode), ctypes.byref(nw), ctypes.byref(nb),
                                     ctypes.byref(lane_out), ctypes.byref(pieces), ctypes.byref(ne), ctypes.byref(entries),
-                                    ctypes.byref(ns), ctypes.byref(supp), cost, ctypes.byref(nst)))
+                                    ctypes.byref(ns), ctypes.byref(supp), cost, ctypes.byref(nst), ctypes.byref(mp)))
     M = (2 * c.L + 1) ** c.dim
-    out = dict(nw=nw.value, nb=nb.value, ns=ns.value, nst=nst.value, cost=list(cost),
+    MAXP = mp.value
+    out = dict(nw=nw.value, nb=nb.value, ns=ns.value, nst=nst.value, cost=list(cost), maxp=MAXP,
                lane_out=np.ctypeslib.as_array(lane_out, (nb.value * 32,)).copy(),
                pieces=np.ctypeslib.as_array(pieces, (nst.value * nw.value * MAXP, 4)).copy(),
                entries=np.ctypeslib.as_array(entries, (max(ne.value, 1), 2)).copy()[:ne.value],
@@ -129,6 +127,7 @@ def replay(c, sched, y1, y2, g, Omega_nu):
     coords = np.stack([(np.arange(M) // strides[d]) % n1 for d in range(dim)], axis=1)   # biased coords
     out = np.zeros((M, J + 1))
     written = np.zeros(M, dtype=int)
+    MAXP = sched["maxp"]
     for sw in range(sched["nst"] * sched["nw"]):      # (stage, warp)
         seen_cont = False
         for q in range(MAXP):
@@ -208,3 +207,44 @@ def test_schedule_geometry_config4():
     # the half-space schedule does half the work of the full one
     full, half = fetch_schedule(c, 0)["cost"], fetch_schedule(c, 2)["cost"]
     assert abs(half[0] / full[0] - 0.5) < 0.01
+
+
+def test_schedule_geometry_config5():
+    """Spiral mean, n = 3, L = J = 6 (BASELINE config 5): 2197 modes = 69 boxes on 12 warps -- more boxes than the
+    four default piece slots per warp.  Every (box, source mode with an in-range lane) pair must appear exactly
+    once, pieces of a box must tile its list, and the half-space schedule must do half the work."""
+    c = ro.OracleRG(ro.default_params(L=6, J=6, torus="spiral"))
+    L, n1, M = 6, 13, 13 ** 3
+    coords = np.stack([(np.arange(M) // n1 ** (2 - d)) % n1 for d in range(3)], axis=1)
+    cost = {}
+    for mode, nout in ((0, M), (2, (M + 1) // 2)):
+        s = fetch_schedule(c, mode)
+        nb = (nout + 31) // 32
+        assert s["nw"] == 12 and s["nst"] == 1 and s["nb"] == nb and s["maxp"] > 4
+        lanes = s["lane_out"]
+        assert sorted(lanes[lanes >= 0]) == list(range(nout))
+        seen = {}
+        for w in range(s["nw"]):
+            conts = 0
+            for q in range(s["maxp"]):
+                box, b, e, rank = s["pieces"][w * s["maxp"] + q]
+                if box < 0:
+                    continue
+                conts += rank > 0
+                seen.setdefault(int(box), []).append((int(rank), int(b), int(e)))
+            assert conts <= 1, "at most one continuation per warp"
+        assert sorted(seen) == list(range(nb))
+        supp = np.nonzero(s["supp"] >= 0)[0]
+        for box, plist in seen.items():
+            plist.sort()
+            assert [r for r, _, _ in plist] == list(range(len(plist)))
+            ents = np.concatenate([s["entries"][b:e] for _, b, e in plist])
+            nu1 = (ents[:, 1] & 0xffff).astype(int)
+            assert len(set(nu1)) == len(nu1)
+            out = lanes[box * 32:(box + 1) * 32]
+            out = out[out >= 0]
+            u = coords[out][:, None, :] - coords[supp][None, :, :] + L          # [lane, source, d]
+            need = ((u >= 0) & (u <= 2 * L)).all(axis=2).any(axis=0)
+            assert sorted(nu1) == sorted(supp[need]), box
+        cost[mode] = s["cost"]
+    assert abs(cost[2][0] / cost[0][0] - 0.5) < 0.01

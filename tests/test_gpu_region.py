@@ -107,6 +107,41 @@ def test_region_spiral_L4J4():
     c.close()
 
 
+def test_global_record_kernel_matches_shared(monkeypatch):
+    """The BIG kernel (operand records in the CTA's global workspace, for arrays beyond one SM's shared memory)
+    forced onto a size that also fits the shared-memory kernel: identical integer maps, same coefficients."""
+    from rg_b200 import RG, make_param_dict
+    from rg_b200.rg_dict import SPIRAL_MEAN
+    g = golden("region_spiral_L4J4_6x6_expm_onestep")
+    p = make_param_dict(L=4, J=4, CanonicalTransformation="expm_onestep", SaveData=False, **SPIRAL_MEAN)
+    c0 = RG(p)
+    h = c0.generate_1Hamiltonian([0.01, 0.05, 0.02], symmetric=True)
+    f_small = c0.rg_map(c0.rg_map(h)).f
+    assert c0.plan_info()["smem_bytes"] > 100000
+    c0.close()
+    monkeypatch.setenv("RG_B200_FORCE_GLOBAL", "1")
+    c1 = RG(p)
+    assert c1.plan_info()["smem_bytes"] < 60000          # only `out` and the reduction scratch stay on chip
+    check_maps(c1, g)
+    f_big = c1.rg_map(c1.rg_map(h)).f
+    # 12 warps instead of 8 cut the source lists at other places (another summation order): roundoff only
+    assert np.abs(f_big - f_small).max() / np.abs(f_small).max() < 1e-13
+    c1.close()
+
+
+def test_points_spiral_L6J6_config5():
+    """BASELINE config 5 (spiral mean n = 3, L = J = 6, expm_multiply): 123 KB per array, 246 KB of g records --
+    runs on the BIG kernel.  Three points frozen from the unmodified reference (RG_modules.point)."""
+    from rg_b200 import RG, make_param_dict, point
+    from rg_b200.rg_dict import SPIRAL_MEAN
+    g = golden("points_spiral_L6J6_expm_multiply")
+    c = RG(make_param_dict(L=6, J=6, CanonicalTransformation="expm_multiply", SaveData=False, **SPIRAL_MEAN))
+    for (x, y), r in zip(g["pts"], g["res"]):
+        (cv, cnt), err = point(x, y, c)
+        assert (cv, cnt, err) == (int(r[0]), int(r[1]), int(r[2])), ((x, y), (cv, cnt, err), r[:3])
+    c.close()
+
+
 def test_point_api_matches_batch():
     from rg_b200 import point
     c = make(5, 5, "expm_onestep")
