@@ -274,57 +274,103 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
     }
 }
 
-// ---- small HBM-bound batched operators (one CTA per Hamiltonian, coalesced over the mode index) ----
-// RG.norm / norm_int / I^- norm (RG.py:92-97,244-247,217-218).  Wrapped layout in, one double out.
-__global__ void __launch_bounds__(256) norm_kernel(const DevPlan P, int n, const double* __restrict__ f, int which, double* __restrict__ out) {
+// ---- small HBM-bound batched operators: one CTA per Hamiltonian, the array streamed in memory order
+// (reference layout [j][wrapped nu]); the per-mode tables are in wrapped order too.  Algorithmic traffic:
+// 8*vecjl bytes per Hamiltonian for a norm, 16*vecjl for sym and re-index (read + write).
+// Every thread keeps RG_SMALL_BATCH independent loads in flight (16 CTAs x 128 threads x 4 x 8 B = 64 KB per SM).
+#define RG_SMALL_THREADS 128
+#define RG_SMALL_BATCH 4
+#define RG_SMALL_STEP(w, j, M) { w += RG_SMALL_THREADS; while (w >= M) { w -= M; ++j; } }
+// RG.norm / norm_int / I^- norm (RG.py:92-97,244-247,217-218).  One double out.
+__global__ void __launch_bounds__(RG_SMALL_THREADS, 16) norm_kernel(const DevPlan P, int n, const double* __restrict__ f, int which, double* __restrict__ out) {
     __shared__ double red[64];
-    const int type = P.norm_choice;
+    const int type = P.norm_choice, M = P.M, V = P.vecjl;
+    int j0 = 0, w0 = threadIdx.x;
+    while (w0 >= M) { w0 -= M; ++j0; }
     for (int item = blockIdx.x; item < n; item += gridDim.x) {
-        const double* fi = f + (size_t)item * P.vecjl;
+        const double* fi = f + (size_t)item * V;
         double p = 0.0, q = 0.0;
-        for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
-            const int j = i / P.M, cidx = i - j * P.M;
-            const int w = P.c2w[cidx];
-            const double v = fi[j * P.M + w];
-            bool use = true;
-            if (which == RG_WHICH_NORM_INT) use = (w != 0);
-            else if (which == RG_WHICH_NORM_IMINUS) use = (P.mask[cidx] >> j) & 1u;
-            if (use) norm_acc(type, p, v, type == 3 ? P.normw[cidx] : 1.0);
+        int j = j0, w = w0;
+        for (int i = threadIdx.x; i < V; i += RG_SMALL_BATCH * RG_SMALL_THREADS) {
+            double v[RG_SMALL_BATCH];
+#pragma unroll
+            for (int u = 0; u < RG_SMALL_BATCH; ++u) { const int k = i + u * RG_SMALL_THREADS; v[u] = k < V ? fi[k] : 0.0; }
+#pragma unroll
+            for (int u = 0; u < RG_SMALL_BATCH; ++u) {
+                if (i + u * RG_SMALL_THREADS < V) {
+                    bool use = true;
+                    if (which == RG_WHICH_NORM_INT) use = (w != 0);
+                    else if (which == RG_WHICH_NORM_IMINUS) use = (P.mask_w[w] >> j) & 1u;
+                    if (use) norm_acc(type, p, v[u], type == 3 ? P.normw_w[w] : 1.0);
+                }
+                RG_SMALL_STEP(w, j, M)
+            }
         }
         double2 r = block_reduce2(red, type, p, q);
         if (threadIdx.x == 0) out[item] = r.x;
     }
 }
 // RG.sym (RG.py:249-253)
-__global__ void __launch_bounds__(256) sym_kernel(const DevPlan P, int n, const double* __restrict__ f, double* __restrict__ out) {
+__global__ void __launch_bounds__(RG_SMALL_THREADS, 16) sym_kernel(const DevPlan P, int n, const double* __restrict__ f, double* __restrict__ out) {
+    const int M = P.M, V = P.vecjl;
+    int j0 = 0, w0 = threadIdx.x;
+    while (w0 >= M) { w0 -= M; ++j0; }
     for (int item = blockIdx.x; item < n; item += gridDim.x) {
-        const double* fi = f + (size_t)item * P.vecjl;
-        double* oi = out + (size_t)item * P.vecjl;
-        for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
-            const int j = i / P.M, cidx = i - j * P.M;
-            const int w = P.c2w[cidx], wm = P.c2w[P.M - 1 - cidx];
-            double v = (fi[j * P.M + w] + fi[j * P.M + wm]) / 2;
-            if (j == 0 && w == 0) v = 0.0;
-            oi[j * P.M + w] = v;
+        const double* fi = f + (size_t)item * V;
+        double* oi = out + (size_t)item * V;
+        int j = j0, w = w0;
+        for (int i = threadIdx.x; i < V; i += RG_SMALL_BATCH * RG_SMALL_THREADS) {
+            double a[RG_SMALL_BATCH], b[RG_SMALL_BATCH];
+#pragma unroll
+            for (int u = 0; u < RG_SMALL_BATCH; ++u) {
+                const int k = i + u * RG_SMALL_THREADS;
+                const bool ok = k < V;
+                a[u] = ok ? fi[k] : 0.0;
+                b[u] = ok ? fi[j * M + P.neg_w[w]] : 0.0;
+                RG_SMALL_STEP(w, j, M)
+            }
+#pragma unroll
+            for (int u = 0; u < RG_SMALL_BATCH; ++u) {
+                const int k = i + u * RG_SMALL_THREADS;
+                if (k < V) oi[k] = (k == 0) ? 0.0 : (a[u] + b[u]) / 2;
+            }
         }
     }
 }
 // head of RG.rg_map (RG.py:210-216)
-__global__ void __launch_bounds__(256) reindex_kernel(const DevPlan P, const Tables T, int n, const double* __restrict__ f, const int* __restrict__ k0, double* __restrict__ out) {
+__global__ void __launch_bounds__(RG_SMALL_THREADS, 16) reindex_kernel(const DevPlan P, const Tables T, int n, const double* __restrict__ f, const int* __restrict__ k0, double* __restrict__ out) {
     __shared__ double ren[32];
+    const int M = P.M, V = P.vecjl;
+    int j0 = 0, w0 = threadIdx.x;
+    while (w0 >= M) { w0 -= M; ++j0; }
     for (int item = blockIdx.x; item < n; item += gridDim.x) {
-        const double* fi = f + (size_t)item * P.vecjl;
-        double* oi = out + (size_t)item * P.vecjl;
+        const double* fi = f + (size_t)item * V;
+        double* oi = out + (size_t)item * V;
         const int k = k0 ? k0[item] : 0;
-        const double f2 = fi[2 * P.M];
+        const double f2 = fi[2 * M];
         const double base = 2 * T.nrm[k] / P.eigenvalue * f2;
         __syncthreads();
         if (threadIdx.x <= P.J) ren[threadIdx.x] = pow(base, (double)(2 - (int)threadIdx.x)) / (2 * f2);
-        __syncthreads();
-        for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
-            const int j = i / P.M, cidx = i - j * P.M;
-            const int s = P.reidx[cidx];
-            oi[j * P.M + P.c2w[cidx]] = (s >= 0 ? fi[j * P.M + P.c2w[s]] : 0.0) * ren[j];
+        int j = j0, w = w0;
+        // the gathers do not depend on the rescaling factors: issue the first batch before waiting for them
+        for (int i0 = 0; i0 < V; i0 += RG_SMALL_BATCH * RG_SMALL_THREADS) {   // CTA-uniform trip count (barrier inside)
+            const int i = i0 + threadIdx.x;
+            double a[RG_SMALL_BATCH];
+            int jj[RG_SMALL_BATCH];
+#pragma unroll
+            for (int u = 0; u < RG_SMALL_BATCH; ++u) {
+                const int kk = i + u * RG_SMALL_THREADS;
+                const int s = P.reidx_w[w];
+                a[u] = (kk < V && s >= 0) ? fi[j * M + s] : 0.0;
+                jj[u] = j;
+                RG_SMALL_STEP(w, j, M)
+            }
+            if (i0 == 0) __syncthreads();
+#pragma unroll
+            for (int u = 0; u < RG_SMALL_BATCH; ++u) {
+                const int kk = i + u * RG_SMALL_THREADS;
+                if (kk < V) oi[kk] = a[u] * ren[min(jj[u], 31)];
+            }
         }
     }
 }
@@ -544,7 +590,23 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
         int l1 = 0; for (int d = 0; d < g.dim; ++d) l1 += std::abs(v[d] - g.L);
         normw[c] = std::exp(prm->norm_analytic * (double)l1);
     }
+    // the same tables in wrapped (memory) order for the stand-alone streaming operators
+    std::vector<uint16_t> mask_w(g.M);
+    std::vector<double> normw_w(g.M);
+    std::vector<int> neg_w(g.M), reidx_w(g.M);
+    for (int c = 0; c < g.M; ++c) {
+        const int w = c2w[c];
+        mask_w[w] = mask[c]; normw_w[w] = normw[c];
+        neg_w[w] = c2w[g.M - 1 - c];
+        reidx_w[w] = prm->reidx[w];
+    }
     int rc;
+    uint16_t* d_mask_w; double* d_normw_w; int* d_neg_w; int* d_reidx_w;
+    if ((rc = dev_upload(p, mask_w.data(), mask_w.size(), &d_mask_w))) return rc;
+    if ((rc = dev_upload(p, normw_w.data(), normw_w.size(), &d_normw_w))) return rc;
+    if ((rc = dev_upload(p, neg_w.data(), neg_w.size(), &d_neg_w))) return rc;
+    if ((rc = dev_upload(p, reidx_w.data(), reidx_w.size(), &d_reidx_w))) return rc;
+    dp.mask_w = d_mask_w; dp.normw_w = d_normw_w; dp.neg_w = d_neg_w; dp.reidx_w = d_reidx_w;
     double* d_om0; uint16_t* d_mask; int* d_reidx; double* d_normw; int* d_c2w; double* d_theta;
     if ((rc = dev_upload(p, om0.data(), om0.size(), &d_om0))) return rc;
     if ((rc = dev_upload(p, mask.data(), mask.size(), &d_mask))) return rc;
@@ -950,7 +1012,7 @@ extern "C" int rg_norm(rg_plan* p, int32_t n, const double* f, int32_t which, do
     if ((rc = st.in(f, sizeof(double) * (size_t)n * p->g.vecjl, &d))) return rc;
     if ((rc = st.outp(out, sizeof(double) * (size_t)n, &o))) return rc;
     if (n > 0) {
-        norm_kernel<<<std::min(n, 148 * 8), 256, 0, p->stream>>>(p->dp, n, (const double*)d, which, (double*)o);
+        norm_kernel<<<std::min(n, p->sm_count * 16), RG_SMALL_THREADS, 0, p->stream>>>(p->dp, n, (const double*)d, which, (double*)o);
         CU(cudaGetLastError());
     }
     return st.finish();
@@ -965,7 +1027,7 @@ extern "C" int rg_sym(rg_plan* p, int32_t n, const double* f, double* out) {
     if ((rc = st.in(f, vb, &d))) return rc;
     if ((rc = st.outp(out, vb, &o))) return rc;
     if (n > 0) {
-        sym_kernel<<<std::min(n, 148 * 8), 256, 0, p->stream>>>(p->dp, n, (const double*)d, (double*)o);
+        sym_kernel<<<std::min(n, p->sm_count * 16), RG_SMALL_THREADS, 0, p->stream>>>(p->dp, n, (const double*)d, (double*)o);
         CU(cudaGetLastError());
     }
     return st.finish();
@@ -981,7 +1043,7 @@ extern "C" int rg_reindex_rescale(rg_plan* p, const rg_tables* tab, int32_t n, c
     if ((rc = st.in(k0, sizeof(int) * (size_t)n, &dk))) return rc;
     if ((rc = st.outp(out, vb, &o))) return rc;
     if (n > 0) {
-        reindex_kernel<<<std::min(n, 148 * 8), 256, 0, p->stream>>>(p->dp, tab->t, n, (const double*)d, (const int*)dk, (double*)o);
+        reindex_kernel<<<std::min(n, p->sm_count * 16), RG_SMALL_THREADS, 0, p->stream>>>(p->dp, tab->t, n, (const double*)d, (const int*)dk, (double*)o);
         CU(cudaGetLastError());
     }
     return st.finish();

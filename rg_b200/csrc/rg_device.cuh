@@ -43,6 +43,11 @@ struct DevPlan {
     const int* reidx;         // [M] centred -> centred source, -1 masked
     const double* normw;      // [M] exp(NormAnalytic*|nu|_1)
     const int* c2w;           // [M] centred -> wrapped index
+    // wrapped-order tables of the stand-alone HBM-bound operators (rg_norm, rg_sym, rg_reindex_rescale)
+    const uint16_t* mask_w;   // [M] I^- bits per Taylor level
+    const double* normw_w;    // [M] exp(NormAnalytic*|nu|_1)
+    const int* neg_w;         // [M] wrapped index of -nu
+    const int* reidx_w;       // [M] wrapped index of sign*N*nu, -1 masked
     const double* theta;
     int n_theta;
     // schedule kind: 0 = I^- support, all modes; 1 = dense (caller-supplied y); 2 = I^- support, half space only

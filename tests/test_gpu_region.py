@@ -142,6 +142,18 @@ def test_points_spiral_L6J6_config5():
     c.close()
 
 
+@pytest.mark.parametrize("ct", ["expm_onestep", "expm_multiply"])
+def test_region_spiral_L6J6_config5(ct):
+    """BASELINE config 5 on the 4x4 strided sub-grid (ix, iy in {16, 48, 80, 112}) of its Nxy=128 region, maps
+    frozen from the unmodified reference."""
+    from rg_b200 import RG, make_param_dict
+    from rg_b200.rg_dict import SPIRAL_MEAN
+    g = golden("region_spiral_L6J6_sub4_" + ct)
+    c = RG(make_param_dict(L=6, J=6, CanonicalTransformation=ct, SaveData=False, **SPIRAL_MEAN))
+    check_maps(c, g)
+    c.close()
+
+
 def test_point_api_matches_batch():
     from rg_b200 import point
     c = make(5, 5, "expm_onestep")
