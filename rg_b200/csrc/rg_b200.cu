@@ -137,7 +137,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
     c.Omega_nu = T.Omega_nu;
     // zero all records once (pads and the all-zero record stay zero for the life of the CTA)
     {
-        const int nd2 = (P.M + 1 + (BIG ? P.M : RG_SCHED(c).n_support)) * P.rec_units;
+        const int nd2 = (P.M + RG_ZERO_RECS + (BIG ? P.M : RG_SCHED(c).n_support)) * P.rec_units;
         for (int i = threadIdx.x; i < nd2; i += blockDim.x) sm.G[i] = make_double2(0.0, 0.0);
     }
     double* fa = c.ws + (size_t)WS_FA * P.vecjl;
@@ -497,7 +497,7 @@ static int rg_warps_for(int M, int J, bool big = false) {
 }
 
 static size_t smem_bytes(const rgplan::Geometry& g, int n_support, bool big) {
-    size_t b = big ? 0 : (size_t)(g.M + 1 + n_support) * g.rec_units * 16;
+    size_t b = big ? 0 : (size_t)(g.M + RG_ZERO_RECS + n_support) * g.rec_units * 16;
     b += (size_t)g.M * g.JP * 8;
     b += 64 * 8 + 16;
     return b;
@@ -571,7 +571,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     dp.max_series = prm->max_series > 0 ? prm->max_series : 100000;
     dp.max_liouville = prm->max_liouville > 0 ? prm->max_liouville : 2000000LL;
     dp.rec_global = big ? 1 : 0;
-    dp.ws_stride = (long long)WS_COUNT * g.vecjl + (big ? (long long)(2 * g.M + 1) * g.rec_units * 2 : 0LL);
+    dp.ws_stride = (long long)WS_COUNT * g.vecjl + (big ? (long long)(2 * g.M + RG_ZERO_RECS) * g.rec_units * 2 : 0LL);
     dp.debug = getenv("RG_B200_DEBUG") ? atoi(getenv("RG_B200_DEBUG")) : 0;
     // centred tables
     std::vector<double> om0(g.M), normw(g.M);

@@ -84,22 +84,26 @@ struct Ctx {
 // BIG kernels (arrays too large for one SM, e.g. n = 3 at L = J = 6: 246 KB of g records alone) keep G and Y in
 // the CTA's global workspace instead -- private to the CTA, read through L1 -- and only `red` and `out` on chip.
 struct Smem {
-    double2* G;   // (M+1) records, the last one all zero
+    double2* G;   // M records followed by RG_ZERO_RECS all-zero ones (out-of-range gathers)
     double2* Y;   // n_support records
     double* out;  // [M][JP]
 };
 #define RG_RED_UNITS 33   // 16-byte units of the `red` block
+// An out-of-range lane gathers the zero record whose index is congruent (mod 8) to the record it would have
+// read: a quarter-warp's eight addresses then stay in eight distinct 16-byte bank groups whatever the mix of
+// in-range and out-of-range lanes (with a single zero record 30 % of the shared-memory wavefronts were replays).
+#define RG_ZERO_RECS 8
 __device__ __forceinline__ double* smem_red() { return reinterpret_cast<double*>(smem_dyn); }
 template <bool BIG>
 __device__ __forceinline__ Smem smem_view(const DevPlan& P, const Sched& S, const Ctx& c) {
     Smem v;
     if (BIG) {
         v.G = c.rec;
-        v.Y = v.G + (P.M + 1) * P.rec_units;
+        v.Y = v.G + (P.M + RG_ZERO_RECS) * P.rec_units;
         v.out = reinterpret_cast<double*>(smem_dyn + RG_RED_UNITS);
     } else {
         v.G = smem_dyn + RG_RED_UNITS;
-        v.Y = v.G + (P.M + 1) * P.rec_units;
+        v.Y = v.G + (P.M + RG_ZERO_RECS) * P.rec_units;
         v.out = reinterpret_cast<double*>(v.Y + S.n_support * P.rec_units);
     }
     return v;
@@ -178,7 +182,7 @@ struct LaneGeo {
     int v0, v1, v2;       // coords + L  (so that v - e, e = biased coord of nu1, is the biased coord of nu - nu1)
     int lin;              // sum_d v_d * stride_d : centred index of (nu - nu1) = lin - index(nu1)
     unsigned lim;         // 2L
-    int zero_rec;         // index of the all-zero record (M)
+    int zero_rec;         // index of the first all-zero record (M)
     uint32_t g_base, y_base;  // shared-memory byte addresses of G and Y (BIG: byte offsets from gb)
     int rec_bytes;
     const char* gb;           // BIG: the CTA's global record block
@@ -192,7 +196,8 @@ __device__ __forceinline__ void decode_entry(const LaneGeo& q, const uint2& me, 
     const unsigned u0 = (unsigned)(q.v0 - (int)(ec & 0xff)), u1 = (unsigned)(q.v1 - (int)((ec >> 8) & 0xff)),
                    u2 = (unsigned)(q.v2 - (int)((ec >> 16) & 0xff));
     const bool ok = max(max(u0, u1), u2) <= q.lim;
-    const int gi = ok ? (q.lin - (int)(ei & 0xffff)) : q.zero_rec;
+    const int nat = q.lin - (int)(ei & 0xffff);
+    const int gi = ok ? nat : q.zero_rec + ((nat - q.zero_rec) & (RG_ZERO_RECS - 1));
     gp = q.g_base + (uint32_t)(gi * q.rec_bytes);
     yp = q.y_base + (uint32_t)((int)(ei >> 16) * q.rec_bytes);
 }
@@ -326,7 +331,7 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     if (BIG) {
         q.gb = reinterpret_cast<const char*>(sm.G);
         q.g_base = 0u;
-        q.y_base = (uint32_t)((P.M + 1) * q.rec_bytes);
+        q.y_base = (uint32_t)((P.M + RG_ZERO_RECS) * q.rec_bytes);
     } else {
         q.gb = nullptr;
         q.g_base = (uint32_t)__cvta_generic_to_shared(sm.G);

@@ -135,6 +135,35 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
             return k * 128 + (uint64_t)v[last];
         };
         std::sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+        // Lane order inside a box.  A quarter-warp's LDS.128 over the gathered records G[nu - nu1] is conflict free
+        // iff its eight record indices are distinct mod 8 (odd record stride in 16-byte units); nu - nu1 shifts all
+        // indices of a box alike, so this is a property of the box.  Sort the box by (index mod 8) and deal the
+        // sorted positions round-robin to the four quarters: a residue class of <= 4 modes never meets itself.
+        // First make every full box hold at most four modes of each residue class: walk the sorted order and let
+        // a mode whose class is already full in the current box wait for the next one (look-ahead of 24 modes, so
+        // boxes keep their shape up to a few swapped cells).
+        {
+            std::vector<int> rest(order), res;
+            res.reserve(order.size());
+            while (!rest.empty()) {
+                int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, taken = 0;
+                std::vector<char> used(rest.size(), 0);
+                const size_t want = std::min<size_t>(32, rest.size());
+                for (size_t i = 0; i < rest.size() && i < 32 + 24 && (size_t)taken < want; ++i)
+                    if (rest.size() < 32 || cnt[rest[i] & 7] < 4) { used[i] = 1; ++cnt[rest[i] & 7]; ++taken; }
+                for (size_t i = 0; i < rest.size() && (size_t)taken < want; ++i)
+                    if (!used[i]) { used[i] = 1; ++taken; }
+                std::vector<int> keep;
+                for (size_t i = 0; i < rest.size(); ++i) { if (used[i]) res.push_back(rest[i]); else keep.push_back(rest[i]); }
+                rest.swap(keep);
+            }
+            order.swap(res);
+        }
+        for (size_t b0 = 0; b0 + 32 <= order.size(); b0 += 32) {
+            std::vector<int> box(order.begin() + b0, order.begin() + b0 + 32);
+            std::stable_sort(box.begin(), box.end(), [](int a, int b) { return (a & 7) < (b & 7); });
+            for (int p = 0; p < 32; ++p) order[b0 + (p % 4) * 8 + p / 4] = box[p];
+        }
         return order;
     };
     auto valid_lanes = [&](const std::vector<int>& order, int b, int c1) {
