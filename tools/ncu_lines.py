@@ -1,0 +1,66 @@
+"""Stall samples of one profiled kernel by CUDA source line and by device function: joins the SASS rows of an
+.ncu-rep source page with nvdisasm's line table of the SAME build of librg_b200.so.
+    python tools/ncu_lines.py gpurun_out/prof.ncu-rep [mangled-substring, default rg_kernelILi10ELb0] [top N]"""
+import csv, os, re, subprocess, sys, tempfile
+from collections import Counter
+
+rep = sys.argv[1]
+sub = sys.argv[2] if len(sys.argv) > 2 else "rg_kernelILi10ELb0"
+topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tmp = tempfile.mkdtemp()
+subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "rg_b200", "librg_b200.so")], cwd=tmp, capture_output=True)
+cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
+dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+lines, cur, on = [], None, False
+for l in dis:
+    if l.startswith(".text."):
+        on = sub in l
+        continue
+    if not on:
+        continue
+    m = re.search(r'//## File "(.*)", line (\d+)', l)
+    if m:
+        cur = (os.path.basename(m.group(1)), int(m.group(2)))
+        continue
+    m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(\S.*);", l)
+    if m:
+        lines.append((int(m.group(1), 16), cur, m.group(2)))
+src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(src.splitlines()))
+h = next(i for i, r in enumerate(rows) if "Source" in r)
+ix = {k: i for i, k in enumerate(rows[h])}
+data = rows[h + 1:]
+assert len(data) == len(lines), (len(data), len(lines), "the report and the library are different builds")
+def num(x):
+    try: return float(x)
+    except ValueError: return 0.0
+# enclosing function of every source line
+funcs = {}
+for fn in ("rg_device.cuh", "rg_multiply.cuh", "rg_b200.cu"):
+    cur_f, tab = "?", []
+    for n, l in enumerate(open(os.path.join(root, "rg_b200", "csrc", fn)), 1):
+        m = re.match(r"^(?:template.*>\s*)?(?:static\s+)?__(?:device|global)__.*?\b(\w+)\s*\(", l)
+        if m: cur_f = m.group(1)
+        tab.append(cur_f)
+    funcs[fn] = tab
+by_line, by_func, stall_f = Counter(), Counter(), {}
+stall_cols = [k for k in ix if k.startswith("stall_") and "Not Issued" not in k]
+tot = 0.0
+for (off, loc, sass), r in zip(lines, data):
+    s = num(r[ix["# Samples"]]); tot += s
+    by_line[loc] += s
+    f = funcs.get(loc[0], ["?"] * 100000)[loc[1] - 1] if loc else "?"
+    by_func[f] += s
+    d = stall_f.setdefault(f, Counter())
+    for k in stall_cols: d[k] += num(r[ix[k]])
+print("total samples %d" % tot)
+print("-- by device function (innermost inlined frame)")
+for f, s in by_func.most_common(16):
+    top = ", ".join("%s %.0f%%" % (k[6:], 100 * v / max(s, 1)) for k, v in stall_f[f].most_common(4))
+    print("%-18s %6.2f%%   %s" % (f, 100 * s / tot, top))
+print("-- by source line")
+for (loc, s) in by_line.most_common(topn):
+    fn, ln = loc if loc else ("?", 0)
+    text = open(os.path.join(root, "rg_b200", "csrc", fn)).read().splitlines()[ln - 1].strip() if loc else ""
+    print("%-16s %5d %6.2f%%  %s" % (fn, ln, 100 * s / tot, text[:100]))
