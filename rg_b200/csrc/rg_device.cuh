@@ -161,6 +161,10 @@ struct RecGeom {
     static constexpr int NP2 = J / 2 + 1;     // y pairs of conv(Omega y, dA g): y2[0..J]
     static constexpr int NP = NP1 + NP2;
     static constexpr int YW = 4;              // prefetch window (pairs)
+    // Every entry runs a branch-free, software-pipelined Taylor product on its zero-padded y record (the absent
+    // levels are stored as exact zeros): entries with jm <= LIM_A levels take the product truncated to LIM_A
+    // levels of y, jm <= LIM_B the one truncated to LIM_B, the rest the complete one.  rgplan::level_class mirrors this.
+    static constexpr int LIM_A = (J >= 8) ? 3 : 0, LIM_B = (J >= 8) ? 6 : 0;
     static constexpr int NPAD = ((NP + YW - 1) / YW) * YW;   // the window must line up across entries
     // double2 unit of the k-th y pair in consumption order (indices >= NP are padding: re-read the last pair)
     __host__ __device__ static constexpr int unit(int k) { return k < NP1 ? k : (k < NP ? ND2 + (k - NP1) : ND2 + NP2 - 1); }
@@ -214,7 +218,9 @@ __device__ __forceinline__ double2 ldrec(const LaneGeo& q, uint32_t addr) {
 // sits inside the DFMA stream (same basic block) so that its latency chain is hidden.
 // yq: window holding pairs 0..YW-1 of this entry on entry, pairs 0..YW-1 of the next entry on exit.
 // gO: Omega-half of this entry's gathered record on entry, of the next entry's on exit.
-template <int J, bool BIG>
+// LIM: Taylor levels of y the entry may have (its record is zero beyond its own jm <= LIM): LIM = J+1 is the
+// complete product; smaller LIM drop the blocks of the absent levels at compile time and keep the load schedule.
+template <int J, bool BIG, int LIM>
 __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
                                             double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& me, int i_next,
                                             bool more, uint32_t& gp, uint32_t& yp, int& jm) {
@@ -235,9 +241,11 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
         if (k < R::NP1) {
             // conv(dA y, Omega g): y1[j1] times B1[j2] = gO[j2]
             const int j1 = 2 * k;
+            if (j1 + 1 < LIM) {     // y1[j1] = (j1+1) y[j1+1]
 #pragma unroll
-            for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, gO[j2], acc[j1 + j2]);
-            if (j1 + 1 < J) {
+                for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, gO[j2], acc[j1 + j2]);
+            }
+            if (j1 + 1 < J && j1 + 2 < LIM) {
 #pragma unroll
                 for (int j2 = 0; j2 <= J - j1 - 1; ++j2) acc[j1 + 1 + j2] = fma(t.y, gO[j2], acc[j1 + 1 + j2]);
             }
@@ -248,9 +256,11 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
         } else {
             // conv(Omega y, dA g): y2[j1] times B2[j2] = gD[j2], j2 < J ; subtracted
             const int j1 = 2 * (k - R::NP1);
+            if (j1 < LIM) {
 #pragma unroll
-            for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, gD[j2], acc[j1 + j2]);
-            if (j1 + 1 <= J) {
+                for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, gD[j2], acc[j1 + j2]);
+            }
+            if (j1 + 1 <= J && j1 + 1 < LIM) {
 #pragma unroll
                 for (int j2 = 0; j2 < J && j1 + 1 + j2 <= J; ++j2) acc[j1 + 1 + j2] = fma(-t.y, gD[j2], acc[j1 + 1 + j2]);
             }
@@ -356,8 +366,10 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
         for (int i = 0; i < cnt; ++i) {
             // the last entry of a chunk prefetches from its own records (harmless, keeps the loop uniform)
             const bool more = (i + 1 < cnt);
-            if (jm == J + 1) taylor_full<J, BIG>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
-            else taylor_partial<J, BIG>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            if (jm > J + 1 || (R::LIM_B == 0 && jm < J + 1)) taylor_partial<J, BIG>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            else if (jm > R::LIM_B) taylor_full<J, BIG, J + 1>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            else if (jm > R::LIM_A) taylor_full<J, BIG, (R::LIM_B > 0 ? R::LIM_B : J + 1)>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            else taylor_full<J, BIG, (R::LIM_A > 0 ? R::LIM_A : J + 1)>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
         }
     }
 }

@@ -61,6 +61,16 @@ inline int taylor_fma(int jm, int J) {
     return c;
 }
 
+// For J >= 8 every list entry runs a branch-free pipelined Taylor product on its zero-padded y record, truncated
+// at compile time to 3, 6 or all J+1 levels of y (measured: the early-exit path costs a complete product whatever
+// the number of levels).  Returns the number of levels the device multiplies for an entry with jm levels present
+// (jm itself on the early-exit path).  Mirrors RecGeom<J>::LIM_A / LIM_B and the dispatch in conv_piece.
+inline int level_class(int jm, int J) {
+    if (jm > J + 1) return jm;          // caller-supplied generator: early-exit path
+    if (J < 8) return jm;               // J+1 -> full path, else early-exit path
+    return jm > 6 ? J + 1 : (jm > 3 ? 6 : 3);
+}
+
 struct Piece { int box, begin, end, rank; };  // rank: position of the piece within its box's list (0 = head)
 
 constexpr int MAXP = 4;    // least number of piece slots per warp and stage: any number of heads (rank 0), at most one continuation
@@ -110,9 +120,10 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
         if (jm > 0) s.supp_rec[c] = s.n_support++;
     }
     auto tcost = [&](int c1) { return (int64_t)taylor_fma(std::min<int>(s.jm[c1], g.JP), J) + (s.jm[c1] > g.JP ? 1 : 0); };
+    auto tissued = [&](int c1) { return s.jm[c1] > g.JP ? tcost(c1) : (int64_t)taylor_fma(level_class(s.jm[c1], J), J); };
     // issue-slot model of one list entry, used to balance the warps: a DFMA holds the issue port ~2.65 cycles on
     // average (operand-reuse misses included), every entry carries ~67 other instructions (loads, decode, loop)
-    auto wcost_of = [&](int c1) { return (int64_t)(2.65 * (double)tcost(c1)) + 67; };
+    auto wcost_of = [&](int c1) { return (int64_t)(2.65 * (double)tissued(c1)) + 67; };
     std::vector<int> outputs;
     for (int c = 0; c < M; ++c) if (!half || c <= c0) outputs.push_back(c);
     const int NO = (int)outputs.size();
@@ -226,10 +237,10 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
                 const int64_t t = tcost(c1);
                 bcost[b] += wcost_of(c1); total += wcost_of(c1);
                 s.fma_useful += (int64_t)nvalid * t;
-                s.fma_executed += 32LL * t;
+                s.fma_executed += 32LL * tissued(c1);
             }
             // entries with every Taylor level present first: the branch-free path then runs in long stretches
-            std::stable_sort(lists[b].begin(), lists[b].end(), [&](int x, int y) { return (s.jm[x] == g.JP) > (s.jm[y] == g.JP); });
+            std::stable_sort(lists[b].begin(), lists[b].end(), [&](int x, int y) { return level_class(s.jm[x], J) > level_class(s.jm[y], J); });
         }
         s.cost_total += total;
         // ---- cluster mode: whole boxes are first partitioned over the `csize` CTAs (contiguous groups, minimal

@@ -203,7 +203,8 @@ def test_schedule_geometry_config4():
         assert s["nw"] == 12 and s["nst"] == 2 and s["nb"] == 2 * nb and s["ns"] == 252
         useful, issued, cmax, ctot = s["cost"]
         assert cmax * s["nw"] <= 1.04 * ctot, "per-warp list costs are balanced to 4%"
-        assert useful / issued > 0.78, "two output partitions keep more than 78% of the issued lanes in range"
+        # issued counts the zero-padded levels of the near-full entries that run the branch-free path
+        assert useful / issued > 0.75, "two output partitions keep more than 75% of the issued lane-FMAs useful"
     # the half-space schedule does half the work of the full one
     full, half = fetch_schedule(c, 0)["cost"], fetch_schedule(c, 2)["cost"]
     assert abs(half[0] / full[0] - 0.5) < 0.01
