@@ -43,6 +43,7 @@ def parse():
                     choices=["expm_onestep", "expm_adapt", "expm_multiply"])
     ap.add_argument("--nxy", type=int, default=GRID["Nxy"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-ct", action="store_true", help="skip the expm_multiply / expm_adapt side measurements")
     ap.add_argument("--cpu-sample", type=int, default=8, help="side of the strided CPU-baseline subsample")
     ap.add_argument("--neighbour-queue", action="store_true", help="experimental: heavy points queue their grid neighbours")
     ap.add_argument("--emulate-world", type=int, default=0,
@@ -132,6 +133,39 @@ def main_reference(a):
 
 
 # ---------------------------------------------------------------------------------------------- our arm
+def other_transformations(a, device):
+    """The three canonical transformations of the reference side by side (RG_dict's default is expm_multiply) on the
+    64x64 strided sub-grid of the same region, device-timed, outside the headline's timed region.  A per-point work
+    budget bounds the few points where expm_multiply's scaling parameter explodes (the reference would spend
+    CPU-hours on each); they are counted in `budget_capped`."""
+    from rg_b200 import RG, make_param_dict
+    from rg_b200 import rg_modules
+    side = 64
+    stride = a.nxy // side
+    out = {}
+    os.environ["RG_B200_MAX_LIOUVILLE"] = "300000"
+    try:
+        for ct in ("expm_onestep", "expm_multiply", "expm_adapt"):
+            case = RG(make_param_dict(L=GRID["L"], J=GRID["J"], Nxy=a.nxy, AmpInf=GRID["AmpInf"], AmpSup=GRID["AmpSup"],
+                                      CanonicalTransformation=ct, SaveData=False), device=device)
+            xs = np.linspace(case.AmpInf[0], case.AmpSup[0], a.nxy)[stride // 2::stride]
+            ys = np.linspace(case.AmpInf[1], case.AmpSup[1], a.nxy)[stride // 2::stride]
+            amps = rg_modules.region_amps(case, xs, ys)
+            case.points(amps[:296])                              # warm-up (plan upload, first launch)
+            conv, count, err = case.points(amps)
+            st = case.last_stats
+            out[ct] = {"value": len(amps) / (st.kernel_ms * 1e-3), "unit": "points/s",
+                       "sample": "%dx%d strided sub-grid (ix,iy = %d, %d, ...) of the Nxy=%d region, work budget 300000 liouville per point"
+                                 % (side, side, stride // 2, stride // 2 + stride, a.nxy),
+                       "liouville_per_point": st.liouville / len(amps),
+                       "useful_tflops": 2.0 * st.conv_fma_useful / st.kernel_ms * 1e-9,
+                       "budget_capped": int((err == -98).sum()), "converged": int(conv.sum()), "count_sum": int(count.sum())}
+            case.close()
+    finally:
+        os.environ.pop("RG_B200_MAX_LIOUVILLE", None)
+    return out
+
+
 def main_b200(a):
     import torch
     import torch.distributed as dist
@@ -248,6 +282,8 @@ def main_b200(a):
         if world == 1 and not a.no_cpu_baseline:
             cb, _, _ = run_cpu(a.ct, a.nxy, a.cpu_sample, 1, 0)
             line["cpu_baseline"] = cb
+        if world == 1 and not a.no_other_ct:
+            line["other_transformations"] = other_transformations(a, local)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
