@@ -62,5 +62,6 @@ for f, s in by_func.most_common(16):
 print("-- by source line")
 for (loc, s) in by_line.most_common(topn):
     fn, ln = loc if loc else ("?", 0)
-    text = open(os.path.join(root, "rg_b200", "csrc", fn)).read().splitlines()[ln - 1].strip() if loc else ""
+    path = os.path.join(root, "rg_b200", "csrc", fn)
+    text = open(path).read().splitlines()[ln - 1].strip() if loc and os.path.exists(path) else ""
     print("%-16s %5d %6.2f%%  %s" % (fn, ln, 100 * s / tot, text[:100]))
