@@ -177,6 +177,9 @@ def main_b200(a):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     case = RG(make_param_dict(L=GRID["L"], J=GRID["J"], Nxy=a.nxy, AmpInf=GRID["AmpInf"], AmpSup=GRID["AmpSup"],
                               CanonicalTransformation=a.ct, SaveData=False), device=local)
