@@ -176,10 +176,12 @@ def main_b200(a):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    # stdout carries exactly one JSON line: everything else written to fd 1 while the job runs (NCCL prints its
+    # version banner there at the first collective) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION/INFO) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO") and not os.environ.get("NCCL_DEBUG_FILE"):
-            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     case = RG(make_param_dict(L=GRID["L"], J=GRID["J"], Nxy=a.nxy, AmpInf=GRID["AmpInf"], AmpSup=GRID["AmpSup"],
                               CanonicalTransformation=a.ct, SaveData=False), device=local)
@@ -287,7 +289,8 @@ def main_b200(a):
             line["cpu_baseline"] = cb
         if world == 1 and not a.no_other_ct:
             line["other_transformations"] = other_transformations(a, local)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
