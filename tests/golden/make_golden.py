@@ -213,6 +213,14 @@ def main(argv):
         over = dict(torus="spiral", L=4, J=4, CT="expm_onestep")
         region_fixture("region_spiral_L4J4_6x6_expm_onestep", over,
                        np.linspace(0, 0.05, 6), np.linspace(0, 0.25, 6))
+    if "norms" in what:
+        # the three other norms of RG.py:92-97 and two stress settings of the tolerances, L=J=5 on the 8x8 grid of G-A's domain
+        xs, ys = np.linspace(0, 0.06, 8), np.linspace(0, 0.08, 8)
+        for tag, extra in (("max", dict(NormChoice="max")), ("Euclidean", dict(NormChoice="Euclidean")),
+                           ("Analytic", dict(NormChoice="Analytic", NormAnalytic=1.0)),
+                           ("maxlie3", dict(MaxLie=3)), ("tolmax1", dict(TolMax=1.0, TolMin=1e-6))):
+            over = dict(L=5, J=5, CT="expm_onestep", **extra)
+            region_fixture("region_L5J5_8x8_" + tag, over, xs, ys)
     if "spiral6" in what:
         # BASELINE config 5 at a checkable size: the 4x4 strided sub-grid (ix, iy in {16, 48, 80, 112}) of the
         # Nxy=128 spiral-mean region, L=J=6 -- about 30-150 s per point and core in the reference

@@ -154,6 +154,56 @@ def test_region_spiral_L6J6_config5(ct):
     c.close()
 
 
+@pytest.mark.parametrize("tag,extra", [("max", dict(NormChoice="max")), ("Euclidean", dict(NormChoice="Euclidean")),
+                                       ("Analytic", dict(NormChoice="Analytic", NormAnalytic=1.0)),
+                                       ("maxlie3", dict(MaxLie=3)), ("tolmax1", dict(TolMax=1.0, TolMin=1e-6))])
+def test_region_L5J5_norms_and_tolerances(tag, extra):
+    """The other three norms of RG.py:92-97, a MaxLie that trips (error -2) and tight TolMax/TolMin, maps frozen
+    from the reference."""
+    g = golden("region_L5J5_8x8_" + tag)
+    c = make(5, 5, "expm_onestep", **extra)
+    check_maps(c, g)
+    c.close()
+
+
+def test_empty_and_tiny_batches():
+    """n = 0 (nothing launched), n = 1, and a ragged n that is no multiple of anything."""
+    g = golden("region_L5J5_12x12_expm_onestep")
+    c = make(5, 5, "expm_onestep")
+    from rg_b200.rg_modules import region_amps
+    amps = region_amps(c, g["xs"], g["ys"])
+    conv, count, err = c.points(amps[:0])
+    assert conv.shape == (0,) and count.shape == (0,) and err.shape == (0,)
+    for n in (1, 37):
+        conv, count, err = c.points(amps[:n])
+        assert np.array_equal(conv, g["conv"].reshape(-1)[:n]) and np.array_equal(count, g["count"].reshape(-1)[:n])
+        assert np.array_equal(err, g["error"].reshape(-1)[:n])
+    c.close()
+
+
+def test_full_grid_config4_checksum():
+    """BASELINE config 4 at full size (Nxy=256, L=J=10, 65 536 points, ~20 s): the 16x16 strided subsample of the
+    result equals the maps frozen from the reference, the run is reproducible bit for bit, and halves computed
+    separately (what two ranks do) give the same arrays."""
+    from rg_b200.rg_modules import region_amps, shard_indices
+    g = golden("region_L10J10_sub16_expm_onestep")
+    c = make(10, 10, "expm_onestep", Nxy=256)
+    xs, ys = np.linspace(0, 0.12, 256), np.linspace(0, 0.35, 256)
+    amps = region_amps(c, xs, ys)
+    conv, count, err = c.points(amps)
+    sub = np.ix_(np.arange(8, 256, 16), np.arange(8, 256, 16))
+    assert np.allclose(xs[8::16], g["xs"]) and np.allclose(ys[8::16], g["ys"])
+    assert np.array_equal(conv.reshape(256, 256)[sub], g["conv"])
+    assert np.array_equal(count.reshape(256, 256)[sub], g["count"])
+    assert np.array_equal(err.reshape(256, 256)[sub], g["error"])
+    assert (int(conv.sum()), int(count.sum())) == (4469, 42835)          # the bench's result_checksum
+    for r in range(2):
+        idx = shard_indices(len(amps), r, 2)
+        cv, cn, er = c.points(amps[idx])
+        assert np.array_equal(cv, conv[idx]) and np.array_equal(cn, count[idx]) and np.array_equal(er, err[idx])
+    c.close()
+
+
 def test_point_api_matches_batch():
     from rg_b200 import point
     c = make(5, 5, "expm_onestep")
