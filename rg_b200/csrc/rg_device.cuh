@@ -163,8 +163,9 @@ struct RecGeom {
     static constexpr int YW = 4;              // prefetch window (pairs)
     // Every entry runs a branch-free, software-pipelined Taylor product on its zero-padded y record (the absent
     // levels are stored as exact zeros): entries with jm <= LIM_A levels take the product truncated to LIM_A
-    // levels of y, jm <= LIM_B the one truncated to LIM_B, the rest the complete one.  rgplan::level_class mirrors this.
-    static constexpr int LIM_A = (J >= 8) ? 3 : 0, LIM_B = (J >= 8) ? 6 : 0;
+    // levels of y, jm <= LIM_B the one truncated to LIM_B, the rest the complete one (J = 10: 3 / 6 / 11 levels,
+    // J = 6: 3 / 5 / 7).  rgplan::level_class mirrors this.
+    static constexpr int LIM_A = (J >= 8) ? 3 : (J / 2 > 2 ? J / 2 : 2), LIM_B = (J >= 8) ? 6 : J - 1;
     static constexpr int NPAD = ((NP + YW - 1) / YW) * YW;   // the window must line up across entries
     // double2 unit of the k-th y pair in consumption order (indices >= NP are padding: re-read the last pair)
     __host__ __device__ static constexpr int unit(int k) { return k < NP1 ? k : (k < NP ? ND2 + (k - NP1) : ND2 + NP2 - 1); }
@@ -366,10 +367,10 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
         for (int i = 0; i < cnt; ++i) {
             // the last entry of a chunk prefetches from its own records (harmless, keeps the loop uniform)
             const bool more = (i + 1 < cnt);
-            if (jm > J + 1 || (R::LIM_B == 0 && jm < J + 1)) taylor_partial<J, BIG>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            if (jm > J + 1) taylor_partial<J, BIG>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);   // caller-supplied y
             else if (jm > R::LIM_B) taylor_full<J, BIG, J + 1>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
-            else if (jm > R::LIM_A) taylor_full<J, BIG, (R::LIM_B > 0 ? R::LIM_B : J + 1)>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
-            else taylor_full<J, BIG, (R::LIM_A > 0 ? R::LIM_A : J + 1)>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            else if (jm > R::LIM_A) taylor_full<J, BIG, R::LIM_B>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
+            else taylor_full<J, BIG, R::LIM_A>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
         }
     }
 }

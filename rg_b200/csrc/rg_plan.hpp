@@ -61,14 +61,14 @@ inline int taylor_fma(int jm, int J) {
     return c;
 }
 
-// For J >= 8 every list entry runs a branch-free pipelined Taylor product on its zero-padded y record, truncated
-// at compile time to 3, 6 or all J+1 levels of y (measured: the early-exit path costs a complete product whatever
+// Every list entry runs a branch-free pipelined Taylor product on its zero-padded y record, truncated at compile
+// time to LIM_A, LIM_B or all J+1 levels of y (measured: the early-exit path costs a complete product whatever
 // the number of levels).  Returns the number of levels the device multiplies for an entry with jm levels present
 // (jm itself on the early-exit path).  Mirrors RecGeom<J>::LIM_A / LIM_B and the dispatch in conv_piece.
 inline int level_class(int jm, int J) {
     if (jm > J + 1) return jm;          // caller-supplied generator: early-exit path
-    if (J < 8) return jm;               // J+1 -> full path, else early-exit path
-    return jm > 6 ? J + 1 : (jm > 3 ? 6 : 3);
+    const int lim_a = (J >= 8) ? 3 : (J / 2 > 2 ? J / 2 : 2), lim_b = (J >= 8) ? 6 : J - 1;
+    return jm > lim_b ? J + 1 : (jm > lim_a ? lim_b : lim_a);
 }
 
 struct Piece { int box, begin, end, rank; };  // rank: position of the piece within its box's list (0 = head)
@@ -105,7 +105,8 @@ struct Schedule {
 // mask[c] = bit j set iff (j, nu_c) in I^- (centred order).  dense: every mode, every level (jm = J+2 so
 // that the y1[J] term of a caller-supplied generator is kept).  half: only modes c <= centre are computed.
 // n_warps: warps of the whole cluster (csize CTAs x warps per CTA).
-inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& mask, bool dense, bool half, int n_warps, int csize = 1) {
+inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t>& mask, bool dense, bool half, int n_warps, int csize,
+                                   bool allow_two_stage) {
     Schedule s;
     const int M = g.M, L = g.L, J = g.J, c0 = (M - 1) / 2;
     s.half = half;
@@ -135,11 +136,18 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
     //   0: (column group of 8 along the last axis, leading axes, column)  -- compact 4 x 8 boxes
     //   1: column-major (last axis slowest)                               -- tall boxes   [2-D only]
     //   2: (column group of 16, row, column)                              -- wide boxes   [2-D only]
+    //   3: centred index order (lines along the last axis)                -- 1 x 1 x 32   [3-D]
+    //   4: blocks of 4 x 1 x 8 (first, second, last axis)                 -- slabs        [3-D]
+    // (3-D, L = J = 6 spiral mean: one partition of 1 x 4 x 8 boxes keeps 0.61 of the issued lanes in range, the
+    //  pair 3 + 4 with every source mode in its cheaper partition 0.72; flat 8 x 4 x 1 blocks would give 0.76 but
+    //  their gathers touch 32 separate cache lines per load when the records live in global memory.)
     auto make_order = [&](int kind) {
         std::vector<int> order = outputs;
         auto key = [&](int c) {
             int v[4]; g.coords(c, v);
             uint64_t k;
+            if (kind == 3) return (uint64_t)c;
+            if (kind == 4) return ((((uint64_t)(v[0] / 4) * 128 + (uint64_t)v[1]) * 128 + (uint64_t)(v[2] / 8)) * 4 + (uint64_t)(v[0] % 4)) * 8 + (uint64_t)(v[2] % 8);
             if (kind == 1) { k = (uint64_t)v[last]; for (int d = 0; d < last; ++d) k = k * 128 + (uint64_t)v[d]; return k; }
             k = (uint64_t)(v[last] / (kind == 2 ? 16 : 8));
             for (int d = 0; d < last; ++d) k = k * 128 + (uint64_t)v[d];
@@ -190,10 +198,10 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
     };
     std::vector<std::vector<int>> orders;
     std::vector<int> stage_of(M, 0);
-    const bool two_stage = (g.dim == 2 && csize == 1 && NBS >= 2);
+    const bool two_stage = (allow_two_stage && (g.dim == 2 || g.dim == 3) && csize == 1 && NBS >= 2);
     if (two_stage) {
-        orders.push_back(make_order(1));
-        orders.push_back(make_order(2));
+        orders.push_back(make_order(g.dim == 2 ? 1 : 3));
+        orders.push_back(make_order(g.dim == 2 ? 2 : 4));
         int64_t n_second = 0;
         for (int c1 = 0; c1 < M; ++c1) {
             if (s.jm[c1] == 0) continue;
@@ -210,7 +218,9 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
     s.n_boxes = NBS * s.n_stages;
     s.n_warps = n_warps > 0 ? n_warps : NBS;
     const int NW = s.n_warps, NWc = NW / csize;
-    s.maxp = std::max(MAXP, (NBS + NWc - 1) / NWc + 2);
+    // piece slots per warp and stage: boxes are dealt by cost, and in three dimensions many boxes are cheap, so a
+    // warp may own any number of them there
+    s.maxp = (g.dim >= 3) ? NBS + 1 : std::max(MAXP, (NBS + NWc - 1) / NWc + 2);
     const int MP = s.maxp;
     s.lane_out.assign(s.n_boxes * 32, -1);
     s.lane_coord.assign(s.n_boxes * 32, 0xFFFFFFFFu);
@@ -313,6 +323,17 @@ inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& ma
     }
     for (int i = 0; i < NW; ++i) { s.cost_max = std::max(s.cost_max, wcost[i]); }
     return s;
+}
+
+// In three dimensions the two-partition schedule is not always the better one (the 8 x 4 x 1 blocks fit a grid of
+// 13^3 modes, not one of 9^3): build both and keep the one that issues fewer FMAs.
+inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& mask, bool dense, bool half, int n_warps, int csize = 1) {
+    Schedule two = make_schedule_impl(g, mask, dense, half, n_warps, csize, true);
+    if (g.dim < 3 || two.n_stages < 2) return two;
+    Schedule one = make_schedule_impl(g, mask, dense, half, n_warps, csize, false);
+    if (two.n_warps < 0) return one;
+    if (one.n_warps < 0) return two;
+    return one.fma_executed <= two.fma_executed ? one : two;
 }
 
 }  // namespace rgplan

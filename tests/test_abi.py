@@ -211,9 +211,10 @@ def test_schedule_geometry_config4():
 
 
 def test_schedule_geometry_config5():
-    """Spiral mean, n = 3, L = J = 6 (BASELINE config 5): 2197 modes = 69 boxes on 12 warps -- more boxes than the
-    four default piece slots per warp.  Every (box, source mode with an in-range lane) pair must appear exactly
-    once, pieces of a box must tile its list, and the half-space schedule must do half the work."""
+    """Spiral mean, n = 3, L = J = 6 (BASELINE config 5): 2197 modes = 69 boxes per partition on 12 warps -- more
+    boxes than the four default piece slots per warp -- and two partitions (lines along the last axis, blocks of
+    8 x 4 x 1).  Every source mode lives in exactly one stage, appears there exactly once in every box that has a
+    lane in range for it, pieces of a box tile its list, and the half-space schedule does half the work."""
     c = ro.OracleRG(ro.default_params(L=6, J=6, torus="spiral"))
     L, n1, M = 6, 13, 13 ** 3
     coords = np.stack([(np.arange(M) // n1 ** (2 - d)) % n1 for d in range(3)], axis=1)
@@ -221,31 +222,44 @@ def test_schedule_geometry_config5():
     for mode, nout in ((0, M), (2, (M + 1) // 2)):
         s = fetch_schedule(c, mode)
         nb = (nout + 31) // 32
-        assert s["nw"] == 12 and s["nst"] == 1 and s["nb"] == nb and s["maxp"] > 4
+        assert s["nw"] == 12 and s["nst"] == 2 and s["nb"] == 2 * nb and s["maxp"] > 4
         lanes = s["lane_out"]
-        assert sorted(lanes[lanes >= 0]) == list(range(nout))
+        for st in range(2):
+            ls = lanes[st * nb * 32:(st + 1) * nb * 32]
+            assert sorted(ls[ls >= 0]) == list(range(nout))
         seen = {}
-        for w in range(s["nw"]):
+        for sw in range(2 * s["nw"]):
             conts = 0
             for q in range(s["maxp"]):
-                box, b, e, rank = s["pieces"][w * s["maxp"] + q]
+                box, b, e, rank = s["pieces"][sw * s["maxp"] + q]
                 if box < 0:
                     continue
+                assert box // nb == sw // s["nw"], "a stage's pieces name that stage's boxes"
                 conts += rank > 0
                 seen.setdefault(int(box), []).append((int(rank), int(b), int(e)))
-            assert conts <= 1, "at most one continuation per warp"
-        assert sorted(seen) == list(range(nb))
+            assert conts <= 1, "at most one continuation per warp and stage"
+        assert set(range(nb)) <= set(seen), "every box of the storing stage has a head"
         supp = np.nonzero(s["supp"] >= 0)[0]
+        stage_of = {}
         for box, plist in seen.items():
             plist.sort()
             assert [r for r, _, _ in plist] == list(range(len(plist)))
             ents = np.concatenate([s["entries"][b:e] for _, b, e in plist])
             nu1 = (ents[:, 1] & 0xffff).astype(int)
             assert len(set(nu1)) == len(nu1)
+            for v in nu1:
+                assert stage_of.setdefault(int(v), box // nb) == box // nb, "a source mode is visited in one stage only"
+        assert sorted(stage_of) == sorted(supp)
+        for box in range(2 * nb):
             out = lanes[box * 32:(box + 1) * 32]
             out = out[out >= 0]
             u = coords[out][:, None, :] - coords[supp][None, :, :] + L          # [lane, source, d]
             need = ((u >= 0) & (u <= 2 * L)).all(axis=2).any(axis=0)
-            assert sorted(nu1) == sorted(supp[need]), box
+            mine = np.array([stage_of[int(v)] == box // nb for v in supp])
+            have = set()
+            for _, b, e in seen.get(box, []):
+                have |= set((s["entries"][b:e, 1] & 0xffff).astype(int))
+            assert have == set(supp[need & mine]), box
         cost[mode] = s["cost"]
+        assert s["cost"][0] / s["cost"][1] > 0.62, "two partitions + level classes keep more than 62% of the issued lane-FMAs useful"
     assert abs(cost[2][0] / cost[0][0] - 0.5) < 0.01
