@@ -213,6 +213,22 @@ def main(argv):
         over = dict(torus="spiral", L=4, J=4, CT="expm_onestep")
         region_fixture("region_spiral_L4J4_6x6_expm_onestep", over,
                        np.linspace(0, 0.05, 6), np.linspace(0, 0.25, 6))
+    if "iterates" in what:
+        # BASELINE config 1: compute_iterates, L=J=5, expm_adapt (RG_dict defaults otherwise).  The reference dies in
+        # case.eigenvalues after the loop (quirk Q1): replace it, and capture what save_data would have written.
+        RG, RG_modules, RG_dict = ref_loader.load()
+        import io, contextlib
+        case = _mk_case(dict(L=5, J=5, CT="expm_adapt", RelDist=1e-7, Iterates=4))
+        case.eigenvalues = lambda *a, **k: None
+        captured = {}
+        orig_save = RG_modules.save_data
+        RG_modules.save_data = lambda name, data, timestr, case_, info=[], display=False: captured.update(data=np.array(data))
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                RG_modules.compute_iterates(case)
+        finally:
+            RG_modules.save_data = orig_save
+        save("iterates_L5J5_adapt", over=repr(dict(L=5, J=5, CT="expm_adapt", RelDist=1e-7, Iterates=4)), data=captured["data"])
     if "norms" in what:
         # the three other norms of RG.py:92-97 and two stress settings of the tolerances, L=J=5 on the 8x8 grid of G-A's domain
         xs, ys = np.linspace(0, 0.06, 8), np.linspace(0, 0.08, 8)

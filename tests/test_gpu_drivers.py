@@ -109,6 +109,21 @@ def test_compute_iterates_runs(tmp_path, monkeypatch, capsys):
     c.close()
 
 
+def test_compute_iterates_matches_reference(tmp_path, monkeypatch, capsys):
+    """BASELINE config 1 frozen from the reference (with its crashing `eigenvalues` call stubbed out): four
+    iterates of (|H - R(H)|, delta, lambda) at RelDist = 1e-7.  delta is a ratio of two distances of order
+    RelDist, so the bisection must take the same decisions as the reference's for it to agree this well."""
+    from rg_b200 import compute_iterates
+    monkeypatch.chdir(tmp_path)
+    g = golden("iterates_L5J5_adapt")
+    c = make(L=5, J=5, CanonicalTransformation="expm_adapt", RelDist=1e-7, Iterates=4, Method="iterates", SaveData=False)
+    data = np.array(compute_iterates(c))
+    capsys.readouterr()
+    assert data.shape == g["data"].shape
+    assert np.allclose(data, g["data"], rtol=1e-5, atol=0), (data, g["data"])
+    c.close()
+
+
 def test_jacobian_columns_match_oracle():
     """the finite-difference Jacobian behind `eigenvalues` as one batch of rg_maps.
     dx = 1e-6 keeps the finite-difference noise (roundoff / dx) below the comparison tolerance."""
