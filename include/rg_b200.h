@@ -135,6 +135,15 @@ int rg_expm(rg_plan* plan, int32_t ct, int32_t n, const double* f, const double*
 int rg_liouville(rg_plan* plan, int32_t n, const double* y0, const double* y1, const double* y2, const double* f,
                  const double* Omega_nu, double* out);
 
+/* RG.approach (RG.py:292-307) for n bracketing pairs at once, the whole bisection on the device: while
+   norm_int(f0 - f1) > reldist * norm(f0): mid = (f0 + f1) * 0.5; RG.converge(mid) replaces f0 (converged) or f1
+   (diverged) and its count / error.  f0, f1 [n][vecjl] and count0/1, err0/1 [n] are in/out (the caller passes the
+   values after RG.approach's `h.error = 0`, RG.py:294-295, and resets err1 afterwards, RG.py:306); levels[n]
+   receives the number of midpoints evaluated.  All pairs share the frequency vector of `tab`.  Every pair
+   advances at its own pace (one CTA or one cluster per pair). */
+int rg_approach(rg_plan* plan, const rg_tables* tab, int32_t n, double* f0, double* f1, double reldist,
+                int32_t* count0, int32_t* count1, int32_t* err0, int32_t* err1, int32_t* levels, rg_stats* stats);
+
 /* RG.conv_product (RG.py:102-106): truncated linear convolution over (j, nu). */
 int rg_conv_product(rg_plan* plan, int32_t n, const double* f1, const double* f2, double* out);
 

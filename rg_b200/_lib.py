@@ -52,6 +52,7 @@ SIGNATURES = {
     "rg_region_work": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, vp, ctypes.c_int32,
                                       ctypes.c_int32, ctypes.POINTER(RGStats)]),
     "rg_converge": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, vp, vp, vp, ctypes.POINTER(RGStats)]),
+    "rg_approach": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_double, vp, vp, vp, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_map": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_expm": (ctypes.c_int, [vp, ctypes.c_int32, ctypes.c_int32, vp, vp, vp, vp, vp, vp, ctypes.c_double, vp, vp,
                                ctypes.POINTER(RGStats)]),

@@ -45,7 +45,8 @@ extern "C" int rg_device_count(int* n) {
 
 // ------------------------------------------------------------------------------------------------ kernels
 struct Job {
-    int mode;  // 0 region (amps), 1 converge (f given), 2 rg_map x n_iter, 3 expm, 4 liouville, 5 generate_y, 6 compute_m_s
+    int mode;  // 0 region (amps), 1 converge (f given), 2 rg_map x n_iter, 3 expm, 4 liouville, 5 generate_y, 6 compute_m_s,
+               // 7 approach (bisection of the pair f_in / f1_io)
     int n;
     int sched;  // 0 sparse, 1 dense (2 = sparse half-space is selected on the device)
     int csize;  // thread-block cluster size: 1, 2 or 4 CTAs per Hamiltonian (modes 0-2 only)
@@ -67,6 +68,8 @@ struct Job {
     // heavy-neighbour scheduling (region grids): a point that turns out heavy queues its grid neighbours
     int* claimed; int* prio_q; int* q_ctr; int row_len; int hot_threshold; int q_cap;
     double* ws_base;
+    // mode 7: the pair is (f_in -> f_out, f1_io); count/err hold the first end, count1/err1 the second
+    double* f1_io; int* count1; int* err1; int* levels; double reldist; int max_levels;
 };
 
 __device__ __forceinline__ void load_wrapped(const DevPlan& P, const double* __restrict__ src, double* __restrict__ dst) {
@@ -254,6 +257,41 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
                 job.m_out[item] = m_star;
                 job.s_out[item] = scale < 2147483647.0 ? (int)scale : 2147483647;
                 job.norm1_out[item] = n1;
+            }
+        } else if (job.mode == 7) {
+            // RG.approach (RG.py:292-307): the whole bisection of one pair, no host round trip per level
+            double* a0 = c.ws + (size_t)WS_A0 * P.vecjl;
+            double* a1 = c.ws + (size_t)WS_A1 * P.vecjl;
+            double* am = c.ws + (size_t)WS_AM * P.vecjl;
+            load_wrapped(P, job.f_in + (size_t)item * P.vecjl, a0);
+            load_wrapped(P, job.f1_io + (size_t)item * P.vecjl, a1);
+            __syncthreads();
+            int cnt0 = job.count[item], cnt1 = job.count1[item], e1 = job.err1[item];
+            int levels = 0, bad = 0;
+            for (;;) {
+                const double2 dn = diff_norms(c, a0, a1, true);
+                if (!(dn.x > job.reldist * dn.y) || levels >= job.max_levels) break;
+                f = fa;
+                for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) { const double m = (a0[i] + a1[i]) * 0.5; am[i] = m; f[i] = m; }
+                __syncthreads();
+                bool cv; int err, status;
+                const int k = converge_dev<J, BIG>(c, f, T, k0, cv, err, status, n_maps);
+                ++levels;
+                if (status) { bad = status == 1 ? RG_ERR_TABLE_EXHAUSTED : RG_ERR_WORK_BUDGET; break; }
+                __syncthreads();
+                copy_arr(c, cv ? a0 : a1, am);
+                if (cv) cnt0 = -k; else { cnt1 = k; e1 = err; }
+                __syncthreads();
+            }
+            if (c.crank == 0) {
+                store_wrapped(P, a0, job.f_out + (size_t)item * P.vecjl);
+                store_wrapped(P, a1, job.f1_io + (size_t)item * P.vecjl);
+                if (threadIdx.x == 0) {
+                    job.count[item] = cnt0; job.count1[item] = cnt1;
+                    job.err1[item] = bad ? bad : e1;
+                    if (bad) job.err[item] = bad;
+                    job.levels[item] = levels;
+                }
             }
         } else if (job.mode == 5) {
             c.Omega_nu = job.Omega_nu;
@@ -801,7 +839,7 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     // of the per-SM throughput (the epilogue is replicated, whole boxes balance to 4:3), so clusters are used
     // only when there are fewer Hamiltonians than SMs: compute_line, approach, small surfaces.
     int csize = 1;
-    if (job.mode <= 2 && p->max_cluster > 1) {
+    if ((job.mode <= 2 || job.mode == 7) && p->max_cluster > 1) {
         if (p->cluster_pref > 0) csize = std::min(p->cluster_pref, p->max_cluster);
         else if ((long long)job.n * 4 <= p->grid_max[s]) csize = std::min(4, p->max_cluster);
         else if ((long long)job.n * 2 <= p->grid_max[s]) csize = 2;
@@ -907,6 +945,27 @@ extern "C" int rg_converge(rg_plan* p, const rg_tables* tab, int32_t n, const do
     if ((rc = st.outp(conv, sizeof(int) * (size_t)n, &o))) return rc; job.conv = (int*)o;
     if ((rc = st.outp(count, sizeof(int) * (size_t)n, &o))) return rc; job.count = (int*)o;
     if ((rc = st.outp(err_io, sizeof(int) * (size_t)n, &o, true))) return rc; job.err = (int*)o;
+    if ((rc = launch_job(p, tab->t, job, stats, st))) return rc;
+    return st.finish();
+}
+
+extern "C" int rg_approach(rg_plan* p, const rg_tables* tab, int32_t n, double* f0, double* f1, double reldist,
+                           int32_t* count0, int32_t* count1, int32_t* err0, int32_t* err1, int32_t* levels, rg_stats* stats) {
+    if (!p || !tab || n < 0 || !f0 || !f1 || !count0 || !count1 || !err0 || !err1 || !levels) return fail(-1, "bad argument");
+    if (p->dp.ct == RG_CT_MULTIPLY && !RG_HAVE_MULTIPLY) return fail(-7, "expm_multiply not available in this build");
+    CU(cudaSetDevice(p->device));
+    Stage st(p);
+    Job job; memset(&job, 0, sizeof(job));
+    job.mode = 7; job.n = n; job.sched = 0; job.reldist = reldist; job.max_levels = 4096;
+    int rc; void* o;
+    const size_t vb = sizeof(double) * (size_t)n * p->g.vecjl, ib = sizeof(int) * (size_t)n;
+    if ((rc = st.outp(f0, vb, &o, true))) return rc; job.f_in = (const double*)o; job.f_out = (double*)o;
+    if ((rc = st.outp(f1, vb, &o, true))) return rc; job.f1_io = (double*)o;
+    if ((rc = st.outp(count0, ib, &o, true))) return rc; job.count = (int*)o;
+    if ((rc = st.outp(count1, ib, &o, true))) return rc; job.count1 = (int*)o;
+    if ((rc = st.outp(err0, ib, &o, true))) return rc; job.err = (int*)o;
+    if ((rc = st.outp(err1, ib, &o, true))) return rc; job.err1 = (int*)o;
+    if ((rc = st.outp(levels, ib, &o))) return rc; job.levels = (int*)o;
     if ((rc = launch_job(p, tab->t, job, stats, st))) return rc;
     return st.finish();
 }

@@ -56,7 +56,9 @@ struct DevPlan {
 };
 
 // workspace arrays of one CTA (each vecjl doubles, layout [j][centred nu])
-enum { WS_FA = 0, WS_FB, WS_Y1, WS_Y2, WS_Y3, WS_H1, WS_H2, WS_T0, WS_T1, WS_T2, WS_T3, WS_T4, WS_T5, WS_T6, WS_T7, WS_T8, WS_COUNT };
+enum { WS_FA = 0, WS_FB, WS_Y1, WS_Y2, WS_Y3, WS_H1, WS_H2, WS_T0, WS_T1, WS_T2, WS_T3, WS_T4, WS_T5, WS_T6, WS_T7, WS_T8,
+       WS_A0, WS_A1, WS_AM,   // RG.approach on the device: the bracketing pair and the midpoint
+       WS_COUNT };
 
 // Plans live in constant memory (uniform-datapath loads inside the device functions); a launch names
 // its plan by slot.  Shared-memory pointers are always re-derived from the __shared__ symbol so that
@@ -598,16 +600,16 @@ __device__ __forceinline__ int expm_onestep(Ctx& c, double* f, double a_unscaled
     return expm_series<J, BIG>(c, f, a_unscaled, step, 1.0, false, 0);
 }
 
-// norm(h1 - h2), norm(h1)
-__device__ __noinline__ double2 diff_norms(const Ctx& c, const double* h1, const double* h2) {
+// norm(h1 - h2), norm(h1); skip_centre: the difference is taken with its nu = 0 column zeroed (RG.norm_int, RG.py:244-247)
+__device__ __noinline__ double2 diff_norms(const Ctx& c, const double* h1, const double* h2, bool skip_centre = false) {
     const DevPlan& P = RG_PLAN(c);
-    const int M = P.M, type = P.norm_choice;
+    const int M = P.M, type = P.norm_choice, c0 = (M - 1) / 2;
     double pd = 0.0, p1 = 0.0;
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
         const double w = (type == 3) ? P.normw[nu] : 1.0;
         for (int j = 0; j <= P.J; ++j) {
             const double a = h1[j * M + nu], b = h2[j * M + nu];
-            norm_acc(type, pd, a - b, w);
+            if (!(skip_centre && nu == c0)) norm_acc(type, pd, a - b, w);
             norm_acc(type, p1, a, w);
         }
     }
@@ -763,6 +765,26 @@ __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, i
     err_out = err;
     norm_int_out = nn.y;
     return f;
+}
+
+// RG.converge (RG.py:278-290) on the array f (WS_FA or WS_FB): iterates rg_map from table row k0 until the
+// interior norm leaves (TolMin, TolMax).  Returns k >= 0 and sets conv; status: 0 ok, 1 table exhausted, 2 work budget.
+template <int J, bool BIG>
+__device__ __forceinline__ int converge_dev(Ctx& c, double*& f, const Tables& T, int k0, bool& conv, int& err, int& status,
+                                            long long& n_maps) {
+    const DevPlan& P = RG_PLAN(c);
+    double2 nn = sym_and_norms(c, f, false);
+    double ni = nn.y;
+    int k = 0;
+    err = 0; status = 0;
+    while (P.tol_max > ni && ni > P.tol_min) {
+        if (k0 + k >= T.n_tab) { status = 1; break; }
+        if (c.n_liou > P.max_liouville) { status = 2; break; }
+        f = rg_map_dev<J, BIG>(c, f, T, k0 + k, err, ni);
+        ++k; ++n_maps;
+    }
+    conv = (ni < P.tol_min) && status == 0;
+    return k;
 }
 
 }  // namespace rgdev

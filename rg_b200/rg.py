@@ -520,6 +520,36 @@ class RG:
         h_list_[1].error = 0
         return h_list_
 
+    def approach_batch(self, pairs, reldist):
+        """RG.approach (RG.py:292-307) for many bracketing pairs in ONE launch: every pair runs its whole
+        bisection on the device (one CTA, or one cluster when there are few pairs) at its own pace -- no lockstep
+        between pairs, no host round trip per level.  Same arithmetic per pair as `approach`: mid = (h0 + h1) * 0.5,
+        `converge(mid)` replaces the end it agrees with.  Returns deep copies like the reference."""
+        pairs = [copy.deepcopy(p) for p in pairs]
+        n = len(pairs)
+        if n == 0:
+            return []
+        nrm, onu, oms, tab = self._tables(pairs[0][0].Omega)
+        for p in pairs:
+            assert xp.array_equal(xp.asarray(p[0].Omega), xp.asarray(pairs[0][0].Omega)), "pairs must share Omega"
+        f0 = xp.stack([_f64(p[0].f).reshape(-1) for p in pairs])
+        f1 = xp.stack([_f64(p[1].f).reshape(-1) for p in pairs])
+        c0 = xp.array([p[0].count for p in pairs], dtype=xp.int32)
+        c1 = xp.array([p[1].count for p in pairs], dtype=xp.int32)
+        e0 = xp.zeros(n, xp.int32)            # `for h in h_list_: h.error = 0`  (RG.py:294-295)
+        e1 = xp.zeros(n, xp.int32)
+        lv = xp.zeros(n, xp.int32)
+        _lib.check(_lib.lib().rg_approach(self._plan(), tab, n, f0.ctypes.data, f1.ctypes.data, float(reldist),
+                                          c0.ctypes.data, c1.ctypes.data, e0.ctypes.data, e1.ctypes.data, lv.ctypes.data,
+                                          self._stats()))
+        for q, p in enumerate(pairs):
+            if e0[q] < 0 or e1[q] <= -98:
+                raise _lib.RGError("approach: pair %d stopped with error %d (iterate table or work budget exhausted)" % (q, min(e0[q], e1[q])))
+            p[0].f, p[0].count, p[0].error = f0[q].reshape(self.r_jl).copy(), int(c0[q]), 0
+            p[1].f, p[1].count, p[1].error = f1[q].reshape(self.r_jl).copy(), int(c1[q]), 0     # RG.py:306
+        self.last_levels = lv
+        return pairs
+
     # ------------------------------------------------------------------ batched region points (RG_modules.py:121-125)
     def K_flat(self):
         n1 = 2 * self.L + 1

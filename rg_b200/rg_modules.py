@@ -7,6 +7,7 @@ and cyclic sharding of the points over the ranks of torch.distributed (one proce
 single final all_gather; `Parallelization` is kept in the dict and ignored.
 """
 import copy
+import os
 import time
 from datetime import date
 
@@ -104,10 +105,11 @@ def compute_cr(epsilon, case):
 
 
 def compute_cr_batch(epsilons, case):
-    """compute_cr for many epsilon at once: the bisections of all columns advance in lockstep, one
-    batched `converge` launch per level (the per-column arithmetic is exactly RG.approach, RG.py:292-307).
-    The reference re-converges the two end points a second time (quirk Q9); the results are identical
-    so that pass is skipped."""
+    """compute_cr for many epsilon at once (RG_modules.py:73-82 per column).  One batched `converge` launch
+    decides which columns are bracketed, then ONE `approach_batch` launch runs every column's whole bisection on
+    the device, each at its own pace (no lockstep between columns; the per-column arithmetic is exactly
+    RG.approach, RG.py:292-307).  The reference re-converges the two end points a second time (quirk Q9); the
+    results are identical so that pass is skipped."""
     n = len(epsilons)
     pairs = []
     for e in epsilons:
@@ -119,31 +121,12 @@ def compute_cr_batch(epsilons, case):
     for i, p in enumerate(pairs):
         c0, c1 = conv[2 * i], conv[2 * i + 1]
         if c0 and not c1:
-            for h in p:
-                h.error = 0
             active.append(i)
         else:
             out[i] = [2 * p[0].f[case.ModesK[0]], xp.nan]
-    while active:
-        h0 = xp.stack([pairs[i][0].f for i in active])
-        h1 = xp.stack([pairs[i][1].f for i in active])
-        d = case.norm_batch(h0 - h1, which=1)
-        nrm = case.norm_batch(h0)
-        still = [i for q, i in enumerate(active) if d[q] > case.RelDist * nrm[q]]
-        for i in active:
-            if i not in still:
-                pairs[i][1].error = 0
-                out[i] = [2 * pairs[i][0].f[_] for _ in case.ModesK]
-        active = still
-        if not active:
-            break
-        mids = [(pairs[i][0] + pairs[i][1]) * 0.5 for i in active]
-        cv = case.converge_batch(mids)
-        for q, i in enumerate(active):
-            if cv[q]:
-                pairs[i][0] = mids[q]
-            else:
-                pairs[i][1] = mids[q]
+    done = case.approach_batch([pairs[i] for i in active], case.RelDist)
+    for i, p in zip(active, done):
+        out[i] = [2 * p[0].f[_] for _ in case.ModesK]
     return out
 
 

@@ -46,6 +46,26 @@ def test_compute_line_L10J10(capsys):
     c.close()
 
 
+def test_approach_batch_matches_host_bisection():
+    """rg_approach (the whole bisection on the device, every pair at its own pace) against RG.approach (host loop
+    around batched converge launches): same brackets, counts and arrays for three different pairs."""
+    c = make(L=5, J=5, CanonicalTransformation="expm_onestep", RelDist=1e-6)
+    pairs = []
+    for e in (0.0, 0.4, 1.0):
+        lo = [e * 0.12, 0.0]
+        hi = [e * 0.12, 0.35]
+        pairs.append([c.generate_1Hamiltonian(lo, symmetric=True), c.generate_1Hamiltonian(hi, symmetric=True)])
+    flags = c.converge_batch([h for p in pairs for h in p])
+    assert flags == [True, False] * 3
+    dev = c.approach_batch(pairs, 1e-6)
+    assert sorted(set(c.last_levels.tolist())) != [0]
+    for p, d in zip(pairs, dev):
+        host = c.approach(p, reldist=1e-6)
+        for a, b in zip(host, d):
+            assert np.array_equal(a.f, b.f) and a.count == b.count and a.error == b.error
+    c.close()
+
+
 def test_compute_surface_L5J5(tmp_path, monkeypatch):
     """G-E: critical surface eps2(eps1), Nxy=8, RelDist=1e-5 (BASELINE config 3 at the CPU-checkable size)."""
     from rg_b200 import compute_surface
