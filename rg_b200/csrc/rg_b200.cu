@@ -135,7 +135,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
     const DevPlan& P = RG_PLAN(c);
     int* sh_item = reinterpret_cast<int*>(smem_red() + 64);
     c.ws = job.ws_base + (size_t)blockIdx.x * (size_t)P.ws_stride;
-    c.rec = reinterpret_cast<double2*>(c.ws + (size_t)WS_COUNT * P.vecjl);
+    c.rec = reinterpret_cast<double2*>(c.ws + (size_t)P.rec_offset);
     const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
     c.Omega_nu = T.Omega_nu;
     // zero all records once (pads and the all-zero record stay zero for the life of the CTA)
@@ -609,7 +609,8 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     dp.max_series = prm->max_series > 0 ? prm->max_series : 100000;
     dp.max_liouville = prm->max_liouville > 0 ? prm->max_liouville : 2000000LL;
     dp.rec_global = big ? 1 : 0;
-    dp.ws_stride = (long long)WS_COUNT * g.vecjl + (big ? (long long)(2 * g.M + RG_ZERO_RECS) * g.rec_units * 2 : 0LL);
+    dp.rec_offset = ((long long)WS_COUNT * g.vecjl + 1) & ~1LL;   // records are read as double2: keep them 16-byte aligned
+    dp.ws_stride = dp.rec_offset + (big ? (long long)(2 * g.M + RG_ZERO_RECS) * g.rec_units * 2 : 0LL);
     dp.debug = getenv("RG_B200_DEBUG") ? atoi(getenv("RG_B200_DEBUG")) : 0;
     // centred tables
     std::vector<double> om0(g.M), normw(g.M);

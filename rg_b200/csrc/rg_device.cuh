@@ -35,7 +35,8 @@ struct DevPlan {
     int max_series;
     long long max_liouville;   // work budget per Hamiltonian (the reference has none, quirk Q6)
     int rec_global;            // 1: the operand records live in the CTA's global workspace (array too large for shared memory)
-    long long ws_stride;       // doubles of workspace per CTA (WS_COUNT arrays + the global records, if any)
+    long long ws_stride;       // doubles of workspace per CTA (WS_COUNT arrays + the global records, if any); even
+    long long rec_offset;      // doubles from a CTA's workspace base to its global records (16-byte aligned)
     int debug;   // RG_B200_DEBUG experiments (0 in production): bit0 gather always hits the zero record,
                  // bit1 every entry broadcasts y record 0
     const double* omega0_nu;  // [M] centred
