@@ -280,7 +280,7 @@ def main_b200(a):
             "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
                          "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, profiles/ncu_bench_traffic_r01.json; "
                                                              "compute-bound kernel: 0.08 % of the HBM peak, L2 write-back of the workspace)",
-                         "kernel": "rg_kernel<10> (fused converge: conv_all + series epilogue)",
+                         "kernel": "rg_kernel<10, false> (fused converge: conv_all + series epilogue)",
                          "peak_source": "measured DFMA peak, tools/fp64_peak.cu on this pool (profiles/fp64_peak_r01.json)",
                          "liouville_evaluations": int(liou_all),
                          "useful_flop_per_liouville": 2 * info["fma_useful_per_liouville"],
