@@ -507,54 +507,75 @@ template <int J, bool BIG>
 __device__ __noinline__ double2 series_epilogue(Ctx& c, double* __restrict__ f, double a0, bool first, double y3mul,
                                                 double y3div, bool use_div, double m) {
     constexpr int JP = J + 1;
+    constexpr int CH = 8;   // items a thread holds between the read and the write phase of a chunk
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M, type = P.norm_choice;
     const bool half = RG_SCHED(c).half != 0;
     const int nmax = half ? (M + 1) / 2 : M;
+    const int total = nmax * JP;
     const double* y3 = c.ws + (size_t)WS_Y3 * P.vecjl;
     const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
     const long long t_begin = clock64();
     double ps = 0.0, pf = 0.0;
-    for (int nu = threadIdx.x; nu < nmax; nu += blockDim.x) {
-        double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
-        const double om = c.Omega_nu[nu];
-        const double w = (type == 3) ? P.normw[nu] : 1.0;
-        const int mu = M - 1 - nu;
-        const bool twin = half && (mu != nu);
-        double sh[JP];
+    // Work item = one coefficient (j, nu), j-major, dealt round-robin to ALL threads of the CTA (a thread per mode
+    // would leave 5 of 12 warps idle on the half-space schedule and serialise 11 levels per thread).  The new
+    // d-type entry r[j-1] = j*sh[j] overwrites what item (j-1, nu) reads as dA g: items are processed in chunks of
+    // CH per thread, reads first, a barrier, then the writes; (j-1, nu) is in the same or an earlier chunk.
+    // (j, nu) of item i = base + q*blockDim + tid, advanced without divisions
+    const int dj = (int)blockDim.x / nmax, dnu = (int)blockDim.x - dj * nmax;
+    int ja = (int)threadIdx.x / nmax, nua = (int)threadIdx.x - ja * nmax;
+    for (int base = 0; base < total; base += CH * (int)blockDim.x) {
+        double v_[CH], fo_[CH];
+        int jb = ja, nub = nua;      // the write phase walks the same items again
 #pragma unroll
-        for (int j = 0; j < JP; ++j) {
-            const double dg = (j < J) ? r[j] : 0.0;
-            double v = a0 * dg + sm.out[nu * JP + j];
-            if (first) {
-                double t = y3[j * M + nu];
-                t = use_div ? t / y3div : t * y3mul;
-                v = t + v;
-            } else {
-                v = v / m;
+        for (int q = 0; q < CH; ++q) {
+            const int i = base + q * (int)blockDim.x + (int)threadIdx.x;
+            const int j = ja, nu = nua;
+            ja += dj; nua += dnu;
+            if (nua >= nmax) { nua -= nmax; ++ja; }
+            v_[q] = 0.0; fo_[q] = 0.0;
+            if (i < total) {
+                const double* r = reinterpret_cast<const double*>(sm.G + nu * P.rec_units);
+                const double dg = (j < J) ? r[j] : 0.0;
+                double v = a0 * dg + sm.out[nu * JP + j];
+                if (first) {
+                    double t = y3[j * M + nu];
+                    t = use_div ? t / y3div : t * y3mul;
+                    v = t + v;
+                } else {
+                    v = v / m;
+                }
+                v_[q] = v;
+                fo_[q] = f[j * M + nu];
             }
-            sh[j] = v;
-            const double fn = f[j * M + nu] + v;
-            f[j * M + nu] = fn;
-            norm_acc(type, ps, v, w);
-            norm_acc(type, pf, fn, w);
-            if (twin) {
-                f[j * M + mu] = fn;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+            const int i = base + q * (int)blockDim.x + (int)threadIdx.x;
+            const int j = jb, nu = nub;
+            jb += dj; nub += dnu;
+            if (nub >= nmax) { nub -= nmax; ++jb; }
+            if (i < total) {
+                const int mu = M - 1 - nu;
+                const bool twin = half && (mu != nu);
+                const double om = c.Omega_nu[nu];
+                const double w = (type == 3) ? P.normw[nu] : 1.0;
+                const double v = v_[q], fn = fo_[q] + v;
+                double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
+                f[j * M + nu] = fn;
                 norm_acc(type, ps, v, w);
                 norm_acc(type, pf, fn, w);
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < JP; ++j) {
-            r[P.off2 + j] = om * sh[j];
-            if (j < J) r[j] = sh[j + 1] * (double)(j + 1);
-        }
-        if (twin) {
-            double* r2 = reinterpret_cast<double*>(sm.G + mu * P.rec_units);
-#pragma unroll
-            for (int j = 0; j < JP; ++j) {
-                r2[P.off2 + j] = -(om * sh[j]);
-                if (j < J) r2[j] = sh[j + 1] * (double)(j + 1);
+                r[P.off2 + j] = om * v;
+                if (j > 0) r[j - 1] = v * (double)j;
+                if (twin) {
+                    double* r2 = reinterpret_cast<double*>(sm.G + mu * P.rec_units);
+                    f[j * M + mu] = fn;
+                    norm_acc(type, ps, v, w);
+                    norm_acc(type, pf, fn, w);
+                    r2[P.off2 + j] = -(om * v);
+                    if (j > 0) r2[j - 1] = v * (double)j;
+                }
             }
         }
     }
