@@ -177,14 +177,14 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
                 f[2 * M + c0] = 0.5;
             }
             __syncthreads();
-            sym_and_norms(c, f, true);
+            sym_and_norms<J>(c, f, true);
         } else if (job.mode != 6) {
             load_wrapped(P, job.f_in + (size_t)item * P.vecjl, f);
             __syncthreads();
         }
         if (job.mode == 0 || job.mode == 1) {
             // RG.converge  RG.py:278-290
-            double2 nn = sym_and_norms(c, f, false);
+            double2 nn = sym_and_norms<J>(c, f, false);
             double ni = nn.y;
             int k = 0, err = 0;
             bool overflow = false, budget = false, hot = false;
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
             } else {
                 // RG.liouville  RG.py:115-117
                 double* dst = c.ws + (size_t)WS_T0 * P.vecjl;
-                build_Y<BIG>(c, 1.0, 1.0, false);
+                build_Y<J, BIG>(c, 1.0, 1.0, false);
                 liouville_apply<J, BIG>(c, f, dst, a, false);
                 __syncthreads();
                 store_wrapped(P, dst, job.f_out + (size_t)item * P.vecjl);
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
             load_wrapped(P, job.y1 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y1 * P.vecjl);
             load_wrapped(P, job.y2 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y2 * P.vecjl);
             __syncthreads();
-            build_Y<BIG>(c, 1.0, 1.0, false);
+            build_Y<J, BIG>(c, 1.0, 1.0, false);
             __syncthreads();
             int m_star; double scale, n1;
             compute_m_s<J, BIG>(c, job.y0[item], m_star, scale, n1);
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
             int cnt0 = job.count[item], cnt1 = job.count1[item], e1 = job.err1[item];
             int levels = 0, bad = 0;
             for (;;) {
-                const double2 dn = diff_norms(c, a0, a1, true);
+                const double2 dn = diff_norms<J>(c, a0, a1, true);
                 if (!(dn.x > job.reldist * dn.y) || levels >= job.max_levels) break;
                 f = fa;
                 for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) { const double m = (a0[i] + a1[i]) * 0.5; am[i] = m; f[i] = m; }
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
             }
         } else if (job.mode == 5) {
             c.Omega_nu = job.Omega_nu;
-            const double a = generate_y(c, f);
+            const double a = generate_y<J>(c, f);
             __syncthreads();
             store_wrapped(P, c.ws + (size_t)WS_Y1 * P.vecjl, job.y1_out + (size_t)item * P.vecjl);
             store_wrapped(P, c.ws + (size_t)WS_Y2 * P.vecjl, job.y2_out + (size_t)item * P.vecjl);

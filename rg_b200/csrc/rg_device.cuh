@@ -461,27 +461,32 @@ __device__ __noinline__ void conv_all(Ctx& c) {
 
 // ------------------------------------------------------------------------------------------------
 // records of g: d-type = dA g (RG.py:76 roll(f*J_,-1)), Omega-type = Omega_nu*g.  src: global [j][nu].
-template <bool BIG>
+// (The per-Lie-step helpers below are templated on J so that their level loops unroll and the J+1 loads of a
+// mode are in flight together: with a run-time J every level waited for its own L2 round trip.)
+template <int J, bool BIG>
 __device__ __noinline__ void build_G(const Ctx& c, const double* __restrict__ src) {
     const DevPlan& P = RG_PLAN(c);
-    const int M = P.M, J = P.J;
+    const int M = P.M;
     const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
         double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
         const double om = c.Omega_nu[nu];
-        double prev = src[nu];
+        double g[J + 1];
+#pragma unroll
+        for (int j = 0; j <= J; ++j) g[j] = src[j * M + nu];
+#pragma unroll
         for (int j = 0; j <= J; ++j) {
-            r[P.off2 + j] = om * prev;
-            if (j < J) { double nx = src[(j + 1) * M + nu]; r[j] = nx * (double)(j + 1); prev = nx; }
+            r[P.off2 + j] = om * g[j];
+            if (j < J) r[j] = g[j + 1] * (double)(j + 1);
         }
     }
 }
 
 // records of y scaled by `step` (item*step, RG.py:176) or divided by `scale` (item/scale, RG.py:156)
-template <bool BIG>
+template <int J, bool BIG>
 __device__ __noinline__ void build_Y(const Ctx& c, double step, double divisor, bool use_div) {
     const DevPlan& P = RG_PLAN(c);
-    const int M = P.M, J = P.J;
+    const int M = P.M;
     const double* y1 = c.ws + (size_t)WS_Y1 * P.vecjl;
     const double* y2 = c.ws + (size_t)WS_Y2 * P.vecjl;
     const Sched& S = RG_SCHED(c);
@@ -490,6 +495,7 @@ __device__ __noinline__ void build_Y(const Ctx& c, double step, double divisor, 
         const int rec = S.supp_rec[nu];
         if (rec < 0) continue;
         double* r = reinterpret_cast<double*>(sm.Y + rec * P.rec_units);
+#pragma unroll
         for (int j = 0; j <= J; ++j) {
             double a = y1[j * M + nu], b = y2[j * M + nu];
             a = use_div ? a / divisor : a * step;
@@ -598,8 +604,8 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
     int err = 0;
     const int sidx_saved = c.sidx;
     if (c.sidx == 0 && c.symm) c.sidx = 2;   // exactly symmetric f and antisymmetric y: compute nu <= 0 only
-    build_Y<BIG>(c, step, divisor, use_div);
-    build_G<BIG>(c, f);
+    build_Y<J, BIG>(c, step, divisor, use_div);
+    build_G<J, BIG>(c, f);
     __syncthreads();
     conv_all<J, BIG>(c);
     double2 r = series_epilogue<J, BIG>(c, f, a0, true, step, divisor, use_div, 1.0);
@@ -623,13 +629,15 @@ __device__ __forceinline__ int expm_onestep(Ctx& c, double* f, double a_unscaled
 }
 
 // norm(h1 - h2), norm(h1); skip_centre: the difference is taken with its nu = 0 column zeroed (RG.norm_int, RG.py:244-247)
+template <int J>
 __device__ __noinline__ double2 diff_norms(const Ctx& c, const double* h1, const double* h2, bool skip_centre = false) {
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M, type = P.norm_choice, c0 = (M - 1) / 2;
     double pd = 0.0, p1 = 0.0;
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
         const double w = (type == 3) ? P.normw[nu] : 1.0;
-        for (int j = 0; j <= P.J; ++j) {
+#pragma unroll
+        for (int j = 0; j <= J; ++j) {
             const double a = h1[j * M + nu], b = h2[j * M + nu];
             if (!(skip_centre && nu == c0)) norm_acc(type, pd, a - b, w);
             norm_acc(type, p1, a, w);
@@ -663,7 +671,7 @@ __device__ __noinline__ int expm_adapt(Ctx& c, double* f, double a_unscaled, dou
         __syncthreads();
         expm_onestep<J, BIG>(c, h2, a_unscaled, 0.5 * s);
         __syncthreads();
-        const double2 r = diff_norms(c, h1, h2);
+        const double2 r = diff_norms<J>(c, h1, h2);
         if (r.x < P.abs_tol + P.rel_tol * r.y) {
             for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) f[i] = 0.75 * h1[i] + 0.25 * h2[i];
             __syncthreads();
@@ -676,9 +684,10 @@ __device__ __noinline__ int expm_adapt(Ctx& c, double* f, double a_unscaled, dou
 }
 
 // RG.generate_y (RG.py:108-113): writes unscaled y1,y2,y3 to WS_Y1..3; returns y[0]
+template <int J>
 __device__ __noinline__ double generate_y(const Ctx& c, const double* __restrict__ f) {
     const DevPlan& P = RG_PLAN(c);
-    const int M = P.M, J = P.J, c0 = (M - 1) / 2;
+    const int M = P.M, c0 = (M - 1) / 2;
     double* y1 = c.ws + (size_t)WS_Y1 * P.vecjl;
     double* y2 = c.ws + (size_t)WS_Y2 * P.vecjl;
     double* y3 = c.ws + (size_t)WS_Y3 * P.vecjl;
@@ -686,12 +695,16 @@ __device__ __noinline__ double generate_y(const Ctx& c, const double* __restrict
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
         const unsigned mk = P.mask[nu];
         const double om0 = P.omega0_nu[nu], om = c.Omega_nu[nu];
+        double fv[J + 1];
+#pragma unroll
+        for (int j = 0; j <= J; ++j) fv[j] = f[j * M + nu];
         double yprev = 0.0;
+#pragma unroll
         for (int j = 0; j <= J; ++j) {
             double y = 0.0;
             if ((mk >> j) & 1u) {
-                if (j == 0) y = f[nu] / om0;
-                else y = (f[j * M + nu] - 2 * f2 * om * yprev) / om0;
+                if (j == 0) y = fv[0] / om0;
+                else y = (fv[j] - 2 * f2 * om * yprev) / om0;
             }
             if (j >= 1) y1[(j - 1) * M + nu] = y * (double)j;
             y2[j * M + nu] = om * y;
@@ -704,6 +717,7 @@ __device__ __noinline__ double generate_y(const Ctx& c, const double* __restrict
 }
 
 // RG.sym (RG.py:249-253) in place, fused with the I^- norm (RG.py:217-218,221) and norm_int (RG.py:244-247)
+template <int J>
 __device__ __noinline__ double2 sym_and_norms(Ctx& c, double* f, bool do_sym) {
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M, type = P.norm_choice, c0 = (M - 1) / 2;
@@ -713,8 +727,12 @@ __device__ __noinline__ double2 sym_and_norms(Ctx& c, double* f, bool do_sym) {
         const int mu = M - 1 - nu;
         const unsigned mk_a = P.mask[nu], mk_b = P.mask[mu];
         const double wa = (type == 3) ? P.normw[nu] : 1.0, wb = (type == 3) ? P.normw[mu] : 1.0;
-        for (int j = 0; j <= P.J; ++j) {
-            double a = f[j * M + nu], b = f[j * M + mu];
+        double fa_[J + 1], fb_[J + 1];
+#pragma unroll
+        for (int j = 0; j <= J; ++j) { fa_[j] = f[j * M + nu]; fb_[j] = f[j * M + mu]; }
+#pragma unroll
+        for (int j = 0; j <= J; ++j) {
+            double a = fa_[j], b = fb_[j];
             if (do_sym) {
                 const double s1 = (a + b) / 2, s2 = (b + a) / 2;
                 a = s1; b = s2;
@@ -736,9 +754,10 @@ __device__ __noinline__ double2 sym_and_norms(Ctx& c, double* f, bool do_sym) {
 }
 
 // head of RG.rg_map (RG.py:210-216): dst = ren[j] * src[j][sign*N*nu] on the mask, else 0
+template <int J>
 __device__ __noinline__ void reindex_rescale(const Ctx& c, const double* __restrict__ src, double* __restrict__ dst, double nrm) {
     const DevPlan& P = RG_PLAN(c);
-    const int M = P.M, J = P.J, c0 = (M - 1) / 2;
+    const int M = P.M, c0 = (M - 1) / 2;
     const double f2 = src[2 * M + c0];
     const double base = 2 * nrm / P.eigenvalue * f2;
     double* red = smem_red();
@@ -746,6 +765,7 @@ __device__ __noinline__ void reindex_rescale(const Ctx& c, const double* __restr
     __syncthreads();
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
         const int s = P.reidx[nu];
+#pragma unroll
         for (int j = 0; j <= J; ++j) dst[j * M + nu] = (s >= 0 ? src[j * M + s] : 0.0) * red[j];
     }
     __syncthreads();
@@ -767,18 +787,18 @@ __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, i
     double* fb = c.ws + (size_t)WS_FB * P.vecjl;
     double* dst = (f == fa) ? fb : fa;
     c.Omega_nu = T.Omega_nu + (size_t)(k + 1) * P.M;
-    reindex_rescale(c, f, dst, T.nrm[k]);
+    reindex_rescale<J>(c, f, dst, T.nrm[k]);
     f = dst;
     int err = 0, kl = 0;
-    double2 nn = sym_and_norms(c, f, false);
+    double2 nn = sym_and_norms<J>(c, f, false);
     while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie && c.n_liou <= P.max_liouville) {
-        const double a = generate_y(c, f);
+        const double a = generate_y<J>(c, f);
         __syncthreads();
         if (P.ct == 0) err = expm_onestep<J, BIG>(c, f, a, 1.0);
         else if (P.ct == 1) err = expm_adapt<J, BIG>(c, f, a, 1.0, err);
         else err = expm_multiply<J, BIG>(c, f, a);
         __syncthreads();
-        nn = sym_and_norms(c, f, true);
+        nn = sym_and_norms<J>(c, f, true);
         ++kl;
         c.n_lie++;
     }
@@ -795,7 +815,7 @@ template <int J, bool BIG>
 __device__ __forceinline__ int converge_dev(Ctx& c, double*& f, const Tables& T, int k0, bool& conv, int& err, int& status,
                                             long long& n_maps) {
     const DevPlan& P = RG_PLAN(c);
-    double2 nn = sym_and_norms(c, f, false);
+    double2 nn = sym_and_norms<J>(c, f, false);
     double ni = nn.y;
     int k = 0;
     err = 0; status = 0;

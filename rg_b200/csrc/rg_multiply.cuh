@@ -18,7 +18,7 @@ __device__ __noinline__ void liouville_apply(Ctx& c, const double* src, double* 
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M;
     const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
-    build_G<BIG>(c, src);
+    build_G<J, BIG>(c, src);
     __syncthreads();
     conv_all<J, BIG>(c);
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
@@ -238,7 +238,7 @@ __device__ __noinline__ void compute_m_s(Ctx& c, double a0, int& m_out, double& 
 template <int J, bool BIG>
 __device__ __noinline__ int expm_multiply(Ctx& c, double* f, double a_unscaled) {
     int m_star; double scale, n1;
-    build_Y<BIG>(c, 1.0, 1.0, false);
+    build_Y<J, BIG>(c, 1.0, 1.0, false);
     __syncthreads();
     compute_m_s<J, BIG>(c, a_unscaled, m_star, scale, n1);
     int err = 0;
