@@ -196,10 +196,11 @@ struct LaneGeo {
     const char* gb;           // BIG: the CTA's global record block
 };
 
-// next entry: broadcast the list words, test nu - nu1 against the grid, form the two record addresses
-__device__ __forceinline__ void decode_entry(const LaneGeo& q, const uint2& me, int i, uint32_t& gp, uint32_t& yp, int& jm) {
-    const uint32_t ec = __shfl_sync(0xffffffffu, me.x, i);
-    const uint32_t ei = __shfl_sync(0xffffffffu, me.y, i);
+// next entry: test nu - nu1 against the grid, form the two record addresses.  w = the entry's two list words, read
+// by every lane from the same address two entries ahead (a warp-wide block of words broadcast by SHFL put the
+// shuffle's latency on the critical path of the short, level-truncated products: 6 % of the stall samples).
+__device__ __forceinline__ void decode_entry(const LaneGeo& q, const uint2& w, uint32_t& gp, uint32_t& yp, int& jm) {
+    const uint32_t ec = w.x, ei = w.y;
     jm = (int)(ec >> 24);
     const unsigned u0 = (unsigned)(q.v0 - (int)(ec & 0xff)), u1 = (unsigned)(q.v1 - (int)((ec >> 8) & 0xff)),
                    u2 = (unsigned)(q.v2 - (int)((ec >> 16) & 0xff));
@@ -226,8 +227,8 @@ __device__ __forceinline__ double2 ldrec(const LaneGeo& q, uint32_t addr) {
 // complete product; smaller LIM drop the blocks of the absent levels at compile time and keep the load schedule.
 template <int J, bool BIG, int LIM>
 __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
-                                            double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& me, int i_next,
-                                            bool more, uint32_t& gp, uint32_t& yp, int& jm) {
+                                            double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& wn,
+                                            uint32_t& gp, uint32_t& yp, int& jm) {
     typedef RecGeom<J> R;
     double gD[2 * R::ND2];
 #pragma unroll
@@ -237,8 +238,7 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
 #pragma unroll
     for (int k = 0; k < R::NPAD; ++k) {
         const double2 t = yq[k % R::YW];
-        if (k == 1) decode_entry(q, me, i_next & 31, gp_n, yp_n, jm_n);   // after the first block has issued; past the
-                                                                        // chunk end this reads a valid dummy entry
+        if (k == 1) decode_entry(q, wn, gp_n, yp_n, jm_n);   // after the first block has issued
         if (k + R::YW < R::NPAD) yq[k % R::YW] = ldrec<BIG>(q, yp + 16 * R::unit(k + R::YW));
         else yq[k % R::YW] = ldrec<BIG>(q, yp_n + 16 * R::unit(k + R::YW - R::NPAD));
         if (k >= R::NP) continue;   // padding pair
@@ -278,8 +278,8 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
 // hand-over protocol of taylor_full (window and gO hold the next entry's data on exit).
 template <int J, bool BIG>
 __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
-                                               double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& me, int i_next,
-                                               bool more, uint32_t& gp, uint32_t& yp, int& jm) {
+                                               double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& wn,
+                                               uint32_t& gp, uint32_t& yp, int& jm) {
     typedef RecGeom<J> R;
     constexpr int JP = J + 1;
     double gD[2 * R::ND2];
@@ -287,7 +287,7 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     for (int u = 0; u < R::ND2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
     uint32_t gp_n = gp, yp_n = yp;
     int jm_n = jm;
-    decode_entry(q, me, i_next & 31, gp_n, yp_n, jm_n);
+    decode_entry(q, wn, gp_n, yp_n, jm_n);
     // conv(dA y, Omega g): y1[j1] = (j1+1) y[j1+1] is non-zero iff j1+1 < jm
 #pragma unroll
     for (int k = 0; k < R::NP1; ++k) {
@@ -355,26 +355,25 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     double2 yq[R::YW];
 #pragma unroll
     for (int j = 0; j <= J; ++j) acc[j] = 0.0;
-    for (int base = e_begin; base < e_end; base += 32) {
-        uint2 me = make_uint2(0u, 0u);
-        if (base + lane < e_end) me = entries[base + lane];
-        const int cnt = min(32, e_end - base);
-        uint32_t gp, yp;
-        int jm;
-        decode_entry(q, me, 0, gp, yp, jm);
+    if (e_begin >= e_end) return;
+    // list words of the current entry, the next one (decoded inside the current product) and the one after
+    // (in flight); past the end the last entry is read again (harmless, keeps the loop uniform)
+    uint2 wn = entries[min(e_begin + 1, e_end - 1)];
+    uint32_t gp, yp;
+    int jm;
+    decode_entry(q, entries[e_begin], gp, yp, jm);
 #pragma unroll
-        for (int u = 0; u < R::NO2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * (R::ND2 + u)); gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
+    for (int u = 0; u < R::NO2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * (R::ND2 + u)); gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
 #pragma unroll
-        for (int k = 0; k < R::YW; ++k) yq[k] = ldrec<BIG>(q, yp + 16 * R::unit(k));
+    for (int k = 0; k < R::YW; ++k) yq[k] = ldrec<BIG>(q, yp + 16 * R::unit(k));
 #pragma unroll 1
-        for (int i = 0; i < cnt; ++i) {
-            // the last entry of a chunk prefetches from its own records (harmless, keeps the loop uniform)
-            const bool more = (i + 1 < cnt);
-            if (jm > J + 1) taylor_partial<J, BIG>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);   // caller-supplied y
-            else if (jm > R::LIM_B) taylor_full<J, BIG, J + 1>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
-            else if (jm > R::LIM_A) taylor_full<J, BIG, R::LIM_B>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
-            else taylor_full<J, BIG, R::LIM_A>(acc, gO, yq, q, me, i + 1, more, gp, yp, jm);
-        }
+    for (int i = e_begin; i < e_end; ++i) {
+        const uint2 wnn = entries[min(i + 2, e_end - 1)];
+        if (jm > J + 1) taylor_partial<J, BIG>(acc, gO, yq, q, wn, gp, yp, jm);   // caller-supplied y
+        else if (jm > R::LIM_B) taylor_full<J, BIG, J + 1>(acc, gO, yq, q, wn, gp, yp, jm);
+        else if (jm > R::LIM_A) taylor_full<J, BIG, R::LIM_B>(acc, gO, yq, q, wn, gp, yp, jm);
+        else taylor_full<J, BIG, R::LIM_A>(acc, gO, yq, q, wn, gp, yp, jm);
+        wn = wnn;
     }
 }
 
