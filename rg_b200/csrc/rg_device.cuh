@@ -366,14 +366,37 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     for (int u = 0; u < R::NO2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * (R::ND2 + u)); gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
 #pragma unroll
     for (int k = 0; k < R::YW; ++k) yq[k] = ldrec<BIG>(q, yp + 16 * R::unit(k));
+    // The planner sorts a list by level class, so a piece is at most three runs: one tight loop per class (its
+    // exit test uses the class of the NEXT entry, known since the decode early in the product) instead of a
+    // dispatch chain per entry.  The outer loop only repeats if a list were not sorted.
+    int i = e_begin;
+    const int last = e_end - 1;
 #pragma unroll 1
-    for (int i = e_begin; i < e_end; ++i) {
-        const uint2 wnn = entries[min(i + 2, e_end - 1)];
-        if (jm > J + 1) taylor_partial<J, BIG>(acc, gO, yq, q, wn, gp, yp, jm);   // caller-supplied y
-        else if (jm > R::LIM_B) taylor_full<J, BIG, J + 1>(acc, gO, yq, q, wn, gp, yp, jm);
-        else if (jm > R::LIM_A) taylor_full<J, BIG, R::LIM_B>(acc, gO, yq, q, wn, gp, yp, jm);
-        else taylor_full<J, BIG, R::LIM_A>(acc, gO, yq, q, wn, gp, yp, jm);
-        wn = wnn;
+    while (i < e_end) {
+#pragma unroll 1
+        while (i < e_end && jm > J + 1) {           // caller-supplied y
+            const uint2 wnn = entries[min(i + 2, last)];
+            taylor_partial<J, BIG>(acc, gO, yq, q, wn, gp, yp, jm);
+            wn = wnn; ++i;
+        }
+#pragma unroll 1
+        while (i < e_end && jm <= J + 1 && jm > R::LIM_B) {
+            const uint2 wnn = entries[min(i + 2, last)];
+            taylor_full<J, BIG, J + 1>(acc, gO, yq, q, wn, gp, yp, jm);
+            wn = wnn; ++i;
+        }
+#pragma unroll 1
+        while (i < e_end && jm <= R::LIM_B && jm > R::LIM_A) {
+            const uint2 wnn = entries[min(i + 2, last)];
+            taylor_full<J, BIG, R::LIM_B>(acc, gO, yq, q, wn, gp, yp, jm);
+            wn = wnn; ++i;
+        }
+#pragma unroll 1
+        while (i < e_end && jm <= R::LIM_A) {
+            const uint2 wnn = entries[min(i + 2, last)];
+            taylor_full<J, BIG, R::LIM_A>(acc, gO, yq, q, wn, gp, yp, jm);
+            wn = wnn; ++i;
+        }
     }
 }
 
