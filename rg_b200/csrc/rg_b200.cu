@@ -17,6 +17,10 @@
 using namespace rgdev;
 
 // Taylor orders J with a compiled kernel (the Taylor loops are fully unrolled per J).
+#ifdef RG_ONLY_J10   // quick experiment builds: nvcc -DRG_ONLY_J10 ... (only the L=J=10 shared-memory kernel)
+#define RG_J_LIST(X) X(10)
+#define RG_JBIG_LIST(X)
+#endif
 #ifndef RG_J_LIST
 #define RG_J_LIST(X) X(4) X(5) X(6) X(10)
 #endif
