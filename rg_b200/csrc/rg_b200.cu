@@ -541,7 +541,8 @@ static int rg_warps_for(int M, int J, bool big = false) {
 static size_t smem_bytes(const rgplan::Geometry& g, int n_support, bool big) {
     size_t b = big ? 0 : (size_t)(g.M + RG_ZERO_RECS + n_support) * g.rec_units * 16;
     b += (size_t)g.M * g.JP * 8;
-    b += 64 * 8 + 16;
+    b += 64 * 8 + 16;            // reduction scratch + work ticket
+    b += RG_CTL_UNITS * 16;      // the convolution's control block
     return b;
 }
 
@@ -600,7 +601,10 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     p->sm_count = prop.multiProcessorCount;
     p->threads = n_warps * 32;
     for (int s = 0; s < 9; ++s)
-        if (p->hs[s].n_warps != (n_warps << (s / 3))) { delete p; return fail(-5, "too many output modes for one CTA's convolution schedule"); }
+        if (p->hs[s].n_warps != (n_warps << (s / 3)) || p->hs[s].n_boxes > RG_MAX_BOXES) {
+            delete p;
+            return fail(-5, "too many output modes for one CTA's convolution schedule");
+        }
     DevPlan& dp = p->dp;
     memset(&dp, 0, sizeof(dp));
     dp.dim = g.dim; dp.L = g.L; dp.J = g.J; dp.JP = g.JP; dp.n1 = g.n1; dp.M = g.M; dp.vecjl = g.vecjl;
@@ -670,8 +674,10 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
         dp.sched[s].n_warps = hs.n_warps; dp.sched[s].n_support = hs.n_support;
         dp.sched[s].maxp = hs.maxp;
         dp.sched[s].n_boxes = hs.n_boxes; dp.sched[s].half = hs.half ? 1 : 0; dp.sched[s].n_stages = hs.n_stages;
-        dp.sched[s].max_rank[0] = hs.max_rank[0]; dp.sched[s].max_rank[1] = hs.max_rank[1];
-        for (int r = 0; r < 4; ++r) { dp.sched[s].fin_begin[r] = hs.fin_begin[r]; dp.sched[s].fin_end[r] = hs.fin_end[r]; }
+        for (int r = 0; r < 4; ++r) {
+            dp.sched[s].fin_begin[r] = hs.fin_begin[r]; dp.sched[s].fin_end[r] = hs.fin_end[r];
+            dp.sched[s].stage0_pieces[r] = hs.stage0_pieces[r];
+        }
         dp.sched[s].lane_out = ds.lane_out; dp.sched[s].lane_coord = ds.lane_coord; dp.sched[s].pieces = ds.pieces;
         dp.sched[s].entries = ds.entries; dp.sched[s].supp_rec = ds.supp_rec;
     }

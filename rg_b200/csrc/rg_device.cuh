@@ -15,8 +15,8 @@ namespace rgdev {
 struct Sched {
     int n_warps, n_boxes, n_support, half, n_stages;
     int maxp;                       // piece slots per warp and stage (rgplan::Schedule::maxp)
-    int max_rank[2];                // per stage
     int fin_begin[4], fin_end[4];   // boxes owned by each CTA of a cluster
+    int stage0_pieces[4];           // pieces each CTA combines in the storing stage
     const int* lane_out;         // [NB*32] centred mode of each lane, -1 idle
     const uint32_t* lane_coord;  // [NB*32] packed biased coords
     const int4* pieces;          // [n_stages][NW*maxp] {box, begin, end, rank}; box = -1 unused; heads first
@@ -92,20 +92,23 @@ struct Smem {
     double* out;  // [M][JP]
 };
 #define RG_RED_UNITS 33   // 16-byte units of the `red` block
+#define RG_CTL_UNITS 64   // 16-byte units of the convolution's control block: 256 ints (per-box rank counters + 1)
+#define RG_MAX_BOXES 250
 // An out-of-range lane gathers the zero record whose index is congruent (mod 8) to the record it would have
 // read: a quarter-warp's eight addresses then stay in eight distinct 16-byte bank groups whatever the mix of
 // in-range and out-of-range lanes (with a single zero record 30 % of the shared-memory wavefronts were replays).
 #define RG_ZERO_RECS 8
 __device__ __forceinline__ double* smem_red() { return reinterpret_cast<double*>(smem_dyn); }
+__device__ __forceinline__ int* smem_ctl() { return reinterpret_cast<int*>(smem_dyn + RG_RED_UNITS); }
 template <bool BIG>
 __device__ __forceinline__ Smem smem_view(const DevPlan& P, const Sched& S, const Ctx& c) {
     Smem v;
     if (BIG) {
         v.G = c.rec;
         v.Y = v.G + (P.M + RG_ZERO_RECS) * P.rec_units;
-        v.out = reinterpret_cast<double*>(smem_dyn + RG_RED_UNITS);
+        v.out = reinterpret_cast<double*>(smem_dyn + RG_RED_UNITS + RG_CTL_UNITS);
     } else {
-        v.G = smem_dyn + RG_RED_UNITS;
+        v.G = smem_dyn + RG_RED_UNITS + RG_CTL_UNITS;
         v.Y = v.G + (P.M + RG_ZERO_RECS) * P.rec_units;
         v.out = reinterpret_cast<double*>(v.Y + S.n_support * P.rec_units);
     }
@@ -401,9 +404,10 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
 }
 
 // out[nu][j] = conv(dA y, Omega g) - conv(Omega y, dA g)  (G, Y in shared memory).  Ends with a barrier.
-// Every warp owns up to S.maxp pieces of the boxes' source lists: heads (rank 0) are stored as they
-// finish, the single continuation a warp may hold (rank r > 0) is added in phase r -- a fixed order, so
-// the result does not depend on timing.  On the half-space schedule only modes nu <= 0 are produced.
+// Every warp owns up to S.maxp pieces of the boxes' source lists per stage: heads (rank 0) store their sums,
+// the single continuation a warp may hold (rank r > 0) adds once the box's counter says r, stage-1 pieces once
+// every stage-0 piece is in -- a fixed order of every sum, so the result does not depend on timing, and no
+// barrier until the end of the bracket.  On the half-space schedule only modes nu <= 0 are produced.
 //
 // Cluster mode (csize = 2 or 4 CTAs per Hamiltonian): every CTA of the cluster runs the whole program on
 // its own copy of the state (bit-identical control flow); only this function is split.  The planner gives
@@ -420,23 +424,34 @@ __device__ __noinline__ void conv_all(Ctx& c) {
     const int vw = c.crank * nwc + w;
     const long long t_begin = clock64();
     if (c.csize > 1) cg::this_cluster().sync();   // every peer has finished reading its `out` of the previous term
+    // Ordered combination without barriers: ctl[b] = number of pieces of box b already combined into its rows,
+    // ctl[n_boxes] = stage-0 pieces combined.  A piece of rank r waits until its box's counter says r (the head
+    // stores, the others add), a stage-1 piece also until every stage-0 piece is in; the order of every sum is
+    // that of the plan, and no warp waits for the slowest one before the end of the bracket.
+    int* const ctl = smem_ctl();
+    volatile int* const vctl = ctl;
+    const int nb_all = S.n_boxes, need0 = S.stage0_pieces[c.crank];
+    for (int i = threadIdx.x; i <= nb_all; i += blockDim.x) ctl[i] = 0;
+    __syncthreads();
     double acc[JP];
-    // stage 0 stores its sums; stage 1 (another partition of the output modes, the remaining source modes)
-    // adds on top once stage 0 is complete
-    for (int st = 0; st < S.n_stages; ++st) {
-        const int4* pieces = S.pieces + (size_t)st * S.n_warps * S.maxp;
-        int4 held = make_int4(-1, 0, 0, 0);
-        const long long t_stage = clock64();
-        if (vw < S.n_warps) {
+    const long long t_stage = clock64();
+    if (vw < S.n_warps) {
+        for (int st = 0; st < S.n_stages; ++st) {
+            const int4* pieces = S.pieces + (size_t)st * S.n_warps * S.maxp;
 #pragma unroll 1
             for (int q = 0; q < S.maxp; ++q) {
-                const int4 p = pieces[vw * S.maxp + q];
+                const int4 p = pieces[vw * S.maxp + q];      // heads first, the continuation (if any) last
                 if (p.x < 0) continue;
-                if (p.w > 0) { held = p; continue; }
                 conv_piece<J, BIG>(c, p.x, p.y, p.z, acc);
+                if (lane == 0) {
+                    if (st) while (vctl[nb_all] < need0) {}
+                    while (vctl[p.x] != p.w) {}
+                }
+                __syncwarp();
+                __threadfence_block();
                 const int nu = S.lane_out[p.x * 32 + lane];
                 if (nu >= 0) {
-                    if (st == 0) {
+                    if (st == 0 && p.w == 0) {
 #pragma unroll
                         for (int j = 0; j < JP; ++j) out[nu * JP + j] = acc[j];
                     } else {
@@ -444,22 +459,17 @@ __device__ __noinline__ void conv_all(Ctx& c) {
                         for (int j = 0; j < JP; ++j) out[nu * JP + j] += acc[j];
                     }
                 }
-            }
-            if (held.x >= 0) conv_piece<J, BIG>(c, held.x, held.y, held.z, acc);
-        }
-        c.t_busy += clock64() - t_stage;
-        __syncthreads();
-        for (int r = 1; r <= S.max_rank[st]; ++r) {
-            if (held.x >= 0 && held.w == r) {
-                const int nu = S.lane_out[held.x * 32 + lane];
-                if (nu >= 0) {
-#pragma unroll
-                    for (int j = 0; j < JP; ++j) out[nu * JP + j] += acc[j];
+                __threadfence_block();   // the rows before the counters
+                __syncwarp();
+                if (lane == 0) {
+                    vctl[p.x] = p.w + 1;
+                    if (st == 0) atomicAdd(&ctl[nb_all], 1);
                 }
             }
-            __syncthreads();
         }
     }
+    c.t_busy += clock64() - t_stage;
+    __syncthreads();
     if (c.csize > 1) {
         cg::cluster_group cl = cg::this_cluster();
         for (int b = S.fin_begin[c.crank] + w; b < S.fin_end[c.crank]; b += nwc) {

@@ -87,6 +87,7 @@ struct Schedule {
     int n_stages = 1;
     int maxp = MAXP;    // piece slots per warp and stage (grows with the number of boxes a warp has to own)
     int fin_begin[4] = {0, 0, 0, 0}, fin_end[4] = {0, 0, 0, 0};   // boxes owned (computed and broadcast) by each CTA (1 stage only)
+    int stage0_pieces[4] = {0, 0, 0, 0};                          // pieces each CTA combines in the storing stage
     int n_boxes = 0;    // boxes of all stages
     int n_support = 0;
     int max_rank[MAXSTAGE] = {0, 0};
@@ -315,6 +316,7 @@ inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t
                         pieces[w * MP + npieces[w]] = pc;
                     }
                     ++npieces[w];
+                    if (st == 0) ++s.stage0_pieces[r];
                     s.max_rank[st] = std::max(s.max_rank[st], rank);
                     ++rank;
                 } while (k < lists[b].size());
