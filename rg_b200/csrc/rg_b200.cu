@@ -617,6 +617,14 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     dp.max_series = prm->max_series > 0 ? prm->max_series : 100000;
     dp.max_liouville = prm->max_liouville > 0 ? prm->max_liouville : 2000000LL;
     dp.rec_global = big ? 1 : 0;
+    {   // mirror shortcuts of generate_y / build_Y need exactly (anti)symmetric tables
+        bool ok = true;
+        for (int c = 0; c < g.M && ok; ++c) {
+            const int m = g.M - 1 - c;
+            ok = mask[c] == mask[m] && prm->omega0_nu[g.wrapped_of_centred(c)] == -prm->omega0_nu[g.wrapped_of_centred(m)];
+        }
+        dp.sym_tables = ok ? 1 : 0;
+    }
     dp.rec_offset = ((long long)WS_COUNT * g.vecjl + 1) & ~1LL;   // records are read as double2: keep them 16-byte aligned
     dp.ws_stride = dp.rec_offset + (big ? (long long)(2 * g.M + RG_ZERO_RECS) * g.rec_units * 2 : 0LL);
     dp.debug = getenv("RG_B200_DEBUG") ? atoi(getenv("RG_B200_DEBUG")) : 0;

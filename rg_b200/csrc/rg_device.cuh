@@ -34,6 +34,7 @@ struct DevPlan {
     double min_step, abs_tol, rel_tol, eigenvalue;
     int max_series;
     long long max_liouville;   // work budget per Hamiltonian (the reference has none, quirk Q6)
+    int sym_tables;            // 1: mask[-nu] == mask[nu], omega0_nu[-nu] == -omega0_nu[nu] exactly (checked by the host)
     int rec_global;            // 1: the operand records live in the CTA's global workspace (array too large for shared memory)
     long long ws_stride;       // doubles of workspace per CTA (WS_COUNT arrays + the global records, if any); even
     long long rec_offset;      // doubles from a CTA's workspace base to its global records (16-byte aligned)
@@ -500,9 +501,14 @@ __device__ __noinline__ void build_G(const Ctx& c, const double* __restrict__ sr
     const DevPlan& P = RG_PLAN(c);
     const int M = P.M;
     const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
-    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+    // exactly symmetric src (c.symm): the thread of nu <= 0 also writes the mirror record (one pass over 221 of the
+    // 441 modes at L = 10 instead of two passes of 384 + 57 threads)
+    const bool mirror = c.symm != 0;
+    const int nmax = mirror ? (M + 1) / 2 : M;
+    for (int nu = threadIdx.x; nu < nmax; nu += blockDim.x) {
         double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
         const double om = c.Omega_nu[nu];
+        const int mu = M - 1 - nu;
         double g[J + 1];
 #pragma unroll
         for (int j = 0; j <= J; ++j) g[j] = src[j * M + nu];
@@ -510,6 +516,14 @@ __device__ __noinline__ void build_G(const Ctx& c, const double* __restrict__ sr
         for (int j = 0; j <= J; ++j) {
             r[P.off2 + j] = om * g[j];
             if (j < J) r[j] = g[j + 1] * (double)(j + 1);
+        }
+        if (mirror && mu != nu) {
+            double* r2 = reinterpret_cast<double*>(sm.G + mu * P.rec_units);
+#pragma unroll
+            for (int j = 0; j <= J; ++j) {
+                r2[P.off2 + j] = -(om * g[j]);
+                if (j < J) r2[j] = g[j + 1] * (double)(j + 1);
+            }
         }
     }
 }
@@ -523,10 +537,15 @@ __device__ __noinline__ void build_Y(const Ctx& c, double step, double divisor, 
     const double* y2 = c.ws + (size_t)WS_Y2 * P.vecjl;
     const Sched& S = RG_SCHED(c);
     const Smem sm = smem_view<BIG>(P, S, c);
-    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+    // y of an exactly symmetric f: y1 = dA y is exactly antisymmetric, y2 = Omega y exactly symmetric
+    const bool mirror = c.symm != 0 && P.sym_tables != 0;
+    const int nmax = mirror ? (M + 1) / 2 : M;
+    for (int nu = threadIdx.x; nu < nmax; nu += blockDim.x) {
         const int rec = S.supp_rec[nu];
         if (rec < 0) continue;
         double* r = reinterpret_cast<double*>(sm.Y + rec * P.rec_units);
+        const int mu = M - 1 - nu;
+        double* r2 = (mirror && mu != nu) ? reinterpret_cast<double*>(sm.Y + S.supp_rec[mu] * P.rec_units) : nullptr;
 #pragma unroll
         for (int j = 0; j <= J; ++j) {
             double a = y1[j * M + nu], b = y2[j * M + nu];
@@ -534,6 +553,7 @@ __device__ __noinline__ void build_Y(const Ctx& c, double step, double divisor, 
             b = use_div ? b / divisor : b * step;
             r[j < J ? j : P.idx_y1J] = a;
             r[P.off2 + j] = b;
+            if (r2) { r2[j < J ? j : P.idx_y1J] = -a; r2[P.off2 + j] = b; }
         }
     }
 }
@@ -724,8 +744,14 @@ __device__ __noinline__ double generate_y(const Ctx& c, const double* __restrict
     double* y2 = c.ws + (size_t)WS_Y2 * P.vecjl;
     double* y3 = c.ws + (size_t)WS_Y3 * P.vecjl;
     const double f2 = f[2 * M + c0], f1 = f[1 * M + c0];
-    for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
+    // exactly symmetric f and antisymmetric omega0_nu, Omega_nu: y[-nu] = -y[nu] exactly (every operation below is
+    // odd or even in the sign flips), so the thread of nu <= 0 writes both modes
+    const bool mirror = c.symm != 0 && P.sym_tables != 0;
+    const int nmax = mirror ? c0 + 1 : M;
+    for (int nu = threadIdx.x; nu < nmax; nu += blockDim.x) {
         const unsigned mk = P.mask[nu];
+        const int mu = M - 1 - nu;
+        const bool twin = mirror && mu != nu;
         const double om0 = P.omega0_nu[nu], om = c.Omega_nu[nu];
         double fv[J + 1];
 #pragma unroll
@@ -738,12 +764,19 @@ __device__ __noinline__ double generate_y(const Ctx& c, const double* __restrict
                 if (j == 0) y = fv[0] / om0;
                 else y = (fv[j] - 2 * f2 * om * yprev) / om0;
             }
-            if (j >= 1) y1[(j - 1) * M + nu] = y * (double)j;
-            y2[j * M + nu] = om * y;
-            y3[j * M + nu] = -om0 * y;
+            const double v1 = y * (double)j, v2 = om * y, v3 = -om0 * y;
+            if (j >= 1) y1[(j - 1) * M + nu] = v1;
+            y2[j * M + nu] = v2;
+            y3[j * M + nu] = v3;
+            if (twin) {
+                if (j >= 1) y1[(j - 1) * M + mu] = -v1;
+                y2[j * M + mu] = v2;
+                y3[j * M + mu] = v3;
+            }
             yprev = y;
         }
         y1[J * M + nu] = 0.0;
+        if (twin) y1[J * M + mu] = 0.0;
     }
     return -f1 / (2 * f2);
 }
