@@ -41,6 +41,12 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 extern "C" const char* rg_last_error(void) { return g_err.c_str(); }
+#ifdef RG_DBG_BUSY   // experiment builds only (tools/probe_region.py PROBE_BUSY=1); not part of include/rg_b200.h
+extern "C" int rg_debug_busy(unsigned long long* out32) {
+    CU(cudaMemcpyFromSymbol(out32, rgdev::g_dbg_busy, 32 * sizeof(unsigned long long)));
+    return 0;
+}
+#endif
 extern "C" int rg_device_count(int* n) {
     cudaError_t e = cudaGetDeviceCount(n);
     if (e != cudaSuccess) { *n = 0; return fail((int)e, cudaGetErrorString(e)); }

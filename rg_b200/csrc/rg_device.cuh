@@ -167,10 +167,16 @@ struct RecGeom {
     static constexpr int NP1 = (J + 1) / 2;   // y pairs of conv(dA y, Omega g): y1[0..J-1]
     static constexpr int NP2 = J / 2 + 1;     // y pairs of conv(Omega y, dA g): y2[0..J]
     static constexpr int NP = NP1 + NP2;
-    // prefetch window (pairs).  2 is the measured optimum: a shorter window leaves ptxas's list scheduler fewer
-    // independent rows to interleave, so more DFMAs keep the operand-reuse hit on y (85 of 130 against 76 with a
-    // window of 4: 52.0 vs 52.7 ms on the uniform batch); shared-memory latency is still covered
-    static constexpr int YW = 2;
+    // prefetch window (pairs).  1 is the measured optimum (uniform batch, L=J=10: 50.0 ms against 50.4 / 50.8 / 52.7 ms
+    // with a window of 2 / 3 / 4): a short window leaves ptxas's list scheduler fewer independent rows to interleave, so
+    // more consecutive DFMAs share the broadcast y operand through the operand-reuse cache (a DFMA with three fresh
+    // 64-bit operands holds the fp64 pipe 3 cycles instead of 2); the other warps of the sub-partition cover the
+    // shared-memory latency.  Forcing the loads into source order (ld.volatile) spreads them perfectly and is 9 % slower:
+    // the reuse hits, not the load latency, decide (tools/sass_reuse.py counts them in a SASS listing).
+#ifndef RG_YW
+#define RG_YW 1
+#endif
+    static constexpr int YW = RG_YW;
     // Every entry runs a branch-free, software-pipelined Taylor product on its zero-padded y record (the absent
     // levels are stored as exact zeros): entries with jm <= LIM_A levels take the product truncated to LIM_A
     // levels of y, jm <= LIM_B the one truncated to LIM_B, the rest the complete one (J = 10: 3 / 6 / 11 levels,
@@ -418,6 +424,9 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
 // each CTA a contiguous group of whole boxes, CTA r computes them exactly as above with its own warps
 // (virtual warps [r*W, (r+1)*W)) and then broadcasts the finished rows into the `out` buffer of every peer
 // through distributed shared memory: two cluster barriers and (csize-1) x its share of `out` per term.
+#ifdef RG_DBG_BUSY
+__device__ unsigned long long g_dbg_busy[32];   // experiment builds: busy clocks of CTA 0's warps in conv_all, [31] = brackets
+#endif
 template <int J, bool BIG>
 __device__ __noinline__ void conv_all(Ctx& c) {
     constexpr int JP = J + 1;
@@ -473,6 +482,10 @@ __device__ __noinline__ void conv_all(Ctx& c) {
         }
     }
     c.t_busy += clock64() - t_stage;
+#ifdef RG_DBG_BUSY
+    if (lane == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[w], (unsigned long long)(clock64() - t_stage));
+    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[31], 1ull);
+#endif
     __syncthreads();
     if (c.csize > 1) {
         cg::cluster_group cl = cg::this_cluster();

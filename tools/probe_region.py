@@ -2,7 +2,9 @@
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-from rg_b200 import RG, make_param_dict
+from rg_b200 import RG, make_param_dict, _lib
+if os.environ.get("PROBE_SO"):   # experiment builds: a variant of librg_b200.so kept next to the product one
+    _lib.SO_PATH = os.path.abspath(os.environ["PROBE_SO"])
 from rg_b200.rg_modules import region_amps
 
 nxy = int(sys.argv[1]) if len(sys.argv) > 1 else 64
@@ -32,3 +34,10 @@ for rep in range(int(os.environ.get('PROBE_REPS', '2'))):
              st.kernel_ms * 1e3 * 148 * info['ctas_per_sm'] / max(st.liouville, 1)))
     print("   clocks per liouville: conv %.0f (warp 0 busy %.0f)  epilogue %.0f  total %.0f" % (st.clk_conv / max(st.liouville, 1), st.clk_conv_busy / max(st.liouville, 1), st.clk_epilogue / max(st.liouville, 1), st.clk_total / max(st.liouville, 1)))
 print("converged %d, errors %s" % (conv.sum(), dict(zip(*np.unique(err, return_counts=True)))))
+if os.environ.get("PROBE_BUSY"):
+    import ctypes
+    from rg_b200 import _lib
+    buf = (ctypes.c_ulonglong * 32)()
+    _lib.lib().rg_debug_busy(buf)
+    n = max(buf[31], 1)
+    print("per-warp busy clocks per bracket (CTA 0):", [round(buf[i] / n) for i in range(12)])
