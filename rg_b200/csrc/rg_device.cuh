@@ -99,6 +99,20 @@ struct Smem {
 // read: a quarter-warp's eight addresses then stay in eight distinct 16-byte bank groups whatever the mix of
 // in-range and out-of-range lanes (with a single zero record 30 % of the shared-memory wavefronts were replays).
 #define RG_ZERO_RECS 8
+#ifdef RG_DBG_BUSY
+// experiment builds: clocks of CTA 0 -- [0..11] busy clocks of its warps in conv_all, [31] = brackets, [16..23] phases
+// of a Lie step as seen by thread 0 (16 generate_y, 17 build_Y + build_G, 18 sym_and_norms, 19 Lie steps)
+__device__ unsigned long long g_dbg_busy[32];
+#define RG_DBG_T0 const long long dbg_t0_ = clock64()
+#define RG_DBG_T1 const long long dbg_t1_ = clock64()
+#define RG_DBG_ADD1(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[slot], (unsigned long long)(clock64() - dbg_t1_)); } while (0)
+#define RG_DBG_ADD(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[slot], (unsigned long long)(clock64() - dbg_t0_)); } while (0)
+#else
+#define RG_DBG_T0
+#define RG_DBG_T1
+#define RG_DBG_ADD1(slot)
+#define RG_DBG_ADD(slot)
+#endif
 __device__ __forceinline__ double* smem_red() { return reinterpret_cast<double*>(smem_dyn); }
 __device__ __forceinline__ int* smem_ctl() { return reinterpret_cast<int*>(smem_dyn + RG_RED_UNITS); }
 template <bool BIG>
@@ -424,11 +438,14 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
 // each CTA a contiguous group of whole boxes, CTA r computes them exactly as above with its own warps
 // (virtual warps [r*W, (r+1)*W)) and then broadcasts the finished rows into the `out` buffer of every peer
 // through distributed shared memory: two cluster barriers and (csize-1) x its share of `out` per term.
-#ifdef RG_DBG_BUSY
-__device__ unsigned long long g_dbg_busy[32];   // experiment builds: busy clocks of CTA 0's warps in conv_all, [31] = brackets
+#ifndef RG_CONV_ATTR
+#define RG_CONV_ATTR __noinline__
+#endif
+#ifndef RG_EPI_ATTR
+#define RG_EPI_ATTR __noinline__
 #endif
 template <int J, bool BIG>
-__device__ __noinline__ void conv_all(Ctx& c) {
+__device__ RG_CONV_ATTR void conv_all(Ctx& c) {
     constexpr int JP = J + 1;
     namespace cg = cooperative_groups;
     const Sched& S = RG_SCHED(c);
@@ -579,7 +596,7 @@ __device__ __noinline__ void build_Y(const Ctx& c, double step, double divisor, 
 // writes the mirror mode -nu (sh, f are exactly symmetric, Omega_nu exactly antisymmetric).
 // SUM: NormChoice = 'sum' (the default) known at compile time -- no norm dispatch, no weights in the item loop.
 template <int J, bool BIG, bool SUM>
-__device__ __noinline__ double2 series_epilogue_impl(Ctx& c, double* __restrict__ f, double a0, bool first, double y3mul,
+__device__ RG_EPI_ATTR double2 series_epilogue_impl(Ctx& c, double* __restrict__ f, double a0, bool first, double y3mul,
                                                      double y3div, bool use_div, double m) {
     constexpr int JP = J + 1;
     constexpr int CH = 8;   // items a thread holds between the read and the write phase of a chunk
@@ -677,17 +694,21 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
     const double tol = 1.1102230246251565e-16;
     const double a0 = use_div ? a_unscaled / divisor : a_unscaled * step;
     int err = 0;
+    RG_DBG_T1;
     const int sidx_saved = c.sidx;
     if (c.sidx == 0 && c.symm) c.sidx = 2;   // exactly symmetric f and antisymmetric y: compute nu <= 0 only
+    { RG_DBG_T0;
     build_Y<J, BIG>(c, step, divisor, use_div);
     build_G<J, BIG>(c, f);
     __syncthreads();
-    conv_all<J, BIG>(c);
-    double2 r = series_epilogue<J, BIG>(c, f, a0, true, step, divisor, use_div, 1.0);
-    double c1 = r.x;
-    for (int m = 2; m_star <= 0 || m <= m_star; ++m) {
+    RG_DBG_ADD(17); }
+    // one loop for all terms (the first one adds y3 and is not divided): conv_all and the epilogue appear once
+    double c1 = 0.0;
+    for (int m = 1; m == 1 || m_star <= 0 || m <= m_star; ++m) {
+        const bool first = (m == 1);
         conv_all<J, BIG>(c);
-        r = series_epilogue<J, BIG>(c, f, a0, false, 0.0, 1.0, false, (double)m);
+        const double2 r = series_epilogue<J, BIG>(c, f, a0, first, first ? step : 0.0, first ? divisor : 1.0, first && use_div, (double)m);
+        if (first) { c1 = r.x; continue; }
         const double c2 = r.x;
         if (c1 + c2 < tol * r.y) break;
         else if (c1 + c2 > P.tol_max) { err = 1; break; }
@@ -695,6 +716,7 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
         if (m >= P.max_series || c.n_liou > P.max_liouville) { err = 1; break; }  // safety: the reference would spin (quirk Q6)
     }
     c.sidx = sidx_saved;
+    RG_DBG_ADD1(21);
     return err;
 }
 
@@ -880,13 +902,19 @@ __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, i
     int err = 0, kl = 0;
     double2 nn = sym_and_norms<J>(c, f, false);
     while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie && c.n_liou <= P.max_liouville) {
-        const double a = generate_y<J>(c, f);
-        __syncthreads();
+        RG_DBG_T1;
+        double a;
+        { RG_DBG_T0; a = generate_y<J>(c, f);
+        __syncthreads(); RG_DBG_ADD(16); }
         if (P.ct == 0) err = expm_onestep<J, BIG>(c, f, a, 1.0);
         else if (P.ct == 1) err = expm_adapt<J, BIG>(c, f, a, 1.0, err);
         else err = expm_multiply<J, BIG>(c, f, a);
-        __syncthreads();
-        nn = sym_and_norms<J>(c, f, true);
+        { RG_DBG_T0; __syncthreads();
+        nn = sym_and_norms<J>(c, f, true); RG_DBG_ADD(18); }
+#ifdef RG_DBG_BUSY
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[19], 1ull);
+#endif
+        RG_DBG_ADD1(20);
         ++kl;
         c.n_lie++;
     }

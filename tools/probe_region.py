@@ -41,3 +41,7 @@ if os.environ.get("PROBE_BUSY"):
     _lib.lib().rg_debug_busy(buf)
     n = max(buf[31], 1)
     print("per-warp busy clocks per bracket (CTA 0):", [round(buf[i] / n) for i in range(12)])
+    ls = max(buf[19], 1)
+    print("clocks per Lie step (CTA 0, thread 0): generate_y %d, build_Y+build_G %d, sym_and_norms %d; brackets per Lie step %.2f"
+          % (buf[16] / ls, buf[17] / ls, buf[18] / ls, n / ls))
+    print("   whole Lie step %d, of which expm_series %d" % (buf[20] / ls, buf[21] / ls))
