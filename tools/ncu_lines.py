@@ -45,6 +45,7 @@ for fn in ("rg_device.cuh", "rg_multiply.cuh", "rg_b200.cu"):
         tab.append(cur_f)
     funcs[fn] = tab
 by_line, by_func, stall_f = Counter(), Counter(), {}
+wave_f, ideal_f, wave_l = Counter(), Counter(), Counter()   # shared-memory wavefronts by function / line
 stall_cols = [k for k in ix if k.startswith("stall_") and "Not Issued" not in k]
 tot = 0.0
 for (off, loc, sass), r in zip(lines, data):
@@ -52,6 +53,9 @@ for (off, loc, sass), r in zip(lines, data):
     by_line[loc] += s
     f = funcs.get(loc[0], ["?"] * 100000)[loc[1] - 1] if loc else "?"
     by_func[f] += s
+    if "L1 Wavefronts Shared" in ix:
+        wave_f[f] += num(r[ix["L1 Wavefronts Shared"]]); ideal_f[f] += num(r[ix["L1 Wavefronts Shared Ideal"]])
+        wave_l[loc] += num(r[ix["L1 Wavefronts Shared"]])
     d = stall_f.setdefault(f, Counter())
     for k in stall_cols: d[k] += num(r[ix[k]])
 print("total samples %d" % tot)
@@ -59,6 +63,17 @@ print("-- by device function (innermost inlined frame)")
 for f, s in by_func.most_common(16):
     top = ", ".join("%s %.0f%%" % (k[6:], 100 * v / max(s, 1)) for k, v in stall_f[f].most_common(4))
     print("%-18s %6.2f%%   %s" % (f, 100 * s / tot, top))
+if wave_f:
+    wt = sum(wave_f.values())
+    print("-- shared-memory wavefronts by device function (total %.3g, ideal %.3g)" % (wt, sum(ideal_f.values())))
+    for f, v in wave_f.most_common(10):
+        print("%-22s %6.2f%%   x%.2f of ideal" % (f, 100 * v / wt, v / max(ideal_f[f], 1)))
+    print("-- shared-memory wavefronts by source line")
+    for loc, v in wave_l.most_common(12):
+        fn, ln = loc if loc else ("?", 0)
+        path = os.path.join(root, "rg_b200", "csrc", fn)
+        text = open(path).read().splitlines()[ln - 1].strip() if loc and os.path.exists(path) else ""
+        print("%-16s %5d %6.2f%%  %s" % (fn, ln, 100 * v / wt, text[:100]))
 print("-- by source line")
 for (loc, s) in by_line.most_common(topn):
     fn, ln = loc if loc else ("?", 0)
