@@ -93,7 +93,7 @@ struct Schedule {
     int max_rank[MAXSTAGE] = {0, 0};
     bool half = false;  // outputs restricted to the half space nu <= 0 (exactly symmetric operands)
     std::vector<int32_t> lane_out;     // [NB*32] centred mode index or -1
-    std::vector<uint32_t> lane_coord;  // [NB*32] packed biased coords (0xFFFFFFFF idle)
+    std::vector<uint32_t> lane_coord;  // [NB*32] packed biased coords (idle lanes: first coordinate 255)
     std::vector<Piece> pieces;         // [n_stages][NW*maxp], box = -1 for unused slots; heads first, continuation last
     std::vector<uint32_t> entries;     // [n*2]: {biased coords of nu1 (8 bits each) | jm<<24, centred index | rec<<16}
     std::vector<int32_t> supp_rec;     // [M] record index of centred nu1, -1 if not in support
@@ -184,6 +184,34 @@ inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t
             std::stable_sort(box.begin(), box.end(), [](int a, int b) { return (a & 7) < (b & 7); });
             for (int p = 0; p < 32; ++p) order[b0 + (p % 4) * 8 + p / 4] = box[p];
         }
+        // The last, partial box (n < 32 modes on lanes 0..n-1: quarters of 8, ..., n mod 8 lanes): the members of a
+        // residue class go to distinct quarters, the roomiest quarter first; only a class with more members than
+        // quarters with room left meets itself.  (Without this the 29-mode tail box of the half-space schedule at
+        // L = 10 paid a second wavefront on three of its four quarter-gathers: 9 % of all gather wavefronts.)
+        {
+            const size_t b0 = order.size() / 32 * 32, n = order.size() - b0;
+            if (n > 0) {
+                std::vector<int> cls[8], quarter[4];
+                for (size_t i = 0; i < n; ++i) cls[order[b0 + i] & 7].push_back(order[b0 + i]);
+                int room[4];
+                for (int q = 0; q < 4; ++q) room[q] = (int)std::min<size_t>(8, n > (size_t)8 * q ? n - 8 * q : 0);
+                int idx[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                std::stable_sort(idx, idx + 8, [&](int a, int b) { return cls[a].size() > cls[b].size(); });
+                std::vector<int> spill;
+                for (int k = 0; k < 8; ++k) {
+                    bool used[4] = {false, false, false, false};
+                    for (int c : cls[idx[k]]) {
+                        int best = -1;
+                        for (int q = 0; q < 4; ++q) if (!used[q] && room[q] > 0 && (best < 0 || room[q] > room[best])) best = q;
+                        if (best < 0) { spill.push_back(c); continue; }
+                        used[best] = true; --room[best]; quarter[best].push_back(c);
+                    }
+                }
+                for (int c : spill) for (int q = 0; q < 4; ++q) if (room[q] > 0) { --room[q]; quarter[q].push_back(c); break; }
+                size_t p = b0;
+                for (int q = 0; q < 4; ++q) for (int c : quarter[q]) order[p++] = c;
+            }
+        }
         return order;
     };
     auto valid_lanes = [&](const std::vector<int>& order, int b, int c1) {
@@ -233,6 +261,20 @@ inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t
         for (int i = 0; i < NO; ++i) {
             s.lane_out[box0 * 32 + i] = order[i];
             int v[4]; g.coords(order[i], v);
+            s.lane_coord[box0 * 32 + i] = g.pack(v);
+        }
+        // Idle lanes of the partial last box: coordinates far outside the grid along the first axis (the lane always
+        // gathers a zero record) and, along the last axis, such that the zero record it picks (index congruent mod 8
+        // to the record it "would have read") is in a bank group none of the quarter's active lanes uses.
+        for (int i = NO; i < NBS * 32; ++i) {
+            const int q0 = i / 8 * 8;
+            bool used[8] = {false, false, false, false, false, false, false, false};
+            for (int l = q0; l < q0 + 8 && l < NO; ++l) used[order[l] & 7] = true;
+            int r = 0;
+            while (r < 7 && used[r]) ++r;
+            int v[4] = {255, 0, 0, 0};
+            v[g.dim - 1] = ((r - 255 * g.stride[0]) % 8 + 8) % 8;
+            if (g.dim == 1) v[0] = 255;   // one axis only: no room for a residue, keep the old convention
             s.lane_coord[box0 * 32 + i] = g.pack(v);
         }
         // ---- per-box union lists of this stage's source modes
