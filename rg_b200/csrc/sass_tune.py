@@ -136,6 +136,7 @@ def main():
             addr, text, lo, hi = insts[i]
             new_hi = hi | YIELD_BIT | REUSE_BIT[slot]
             data[pos + 24:pos + 32] = struct.pack('<Q', new_hi)
+            insts[i][3] = new_hi          # the windows of its neighbours must match the patched bytes
             o = operands(text)
             o[slot] += '.reuse'
             expect[(name, addr)] = 'DFMA ' + ', '.join(o)

@@ -263,3 +263,42 @@ def test_schedule_geometry_config5():
         cost[mode] = s["cost"]
         assert s["cost"][0] / s["cost"][1] > 0.62, "two partitions + level classes keep more than 62% of the issued lane-FMAs useful"
     assert abs(cost[2][0] / cost[0][0] - 0.5) < 0.01
+
+
+def test_gathers_of_config4_are_bank_conflict_free():
+    """A quarter-warp's LDS.128 over the gathered records G[nu - nu1] is conflict free iff the eight record indices
+    are distinct mod 8 (odd record stride in 16-byte units).  nu - nu1 shifts every lane of a box alike, so the lanes
+    of every quarter of every box -- the partial last box of a stage included -- must carry eight distinct residues
+    of the centred index (rg_plan.hpp: residue-balanced boxes, sorted positions dealt to the quarters)."""
+    c = ro.OracleRG(ro.default_params(L=10, J=10))
+    for mode in (0, 2):
+        s = fetch_schedule(c, mode)
+        lanes = s["lane_out"].reshape(-1, 4, 8)
+        for box in range(lanes.shape[0]):
+            for q in range(4):
+                act = lanes[box, q][lanes[box, q] >= 0]
+                assert len(set(act & 7)) == len(act), (mode, box, q, sorted(act & 7))
+
+
+def test_sass_tune_round_trip(tmp_path):
+    """rg_b200/csrc/sass_tune.py (opt-in, `make SASS_TUNE=1`) on a copy of the built library: it finds yield-hinted
+    DFMAs in the hot loops, patches control bits only, and its own re-disassembly check accepts the result."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    so = tmp_path / "librg_b200_copy.so"
+    shutil.copy(_lib.SO_PATH, so)
+    before = so.read_bytes()
+    tool = os.path.join(ROOT, "rg_b200", "csrc", "sass_tune.py")
+    r = subprocess.run([sys.executable, tool, str(so)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    m = re.search(r"sass_tune: (\d+) DFMA retuned", r.stdout)
+    assert m and int(m.group(1)) >= 20, r.stdout
+    after = so.read_bytes()
+    assert len(after) == len(before)
+    diff = [i for i in range(len(before)) if before[i] != after[i]]
+    assert 0 < len(diff) <= 2 * int(m.group(1)), "only control bytes of the retuned instructions may change"
+    # a second pass finds nothing left to do in the kernels it already tuned
+    r2 = subprocess.run([sys.executable, tool, str(so), "--dry-run"], capture_output=True, text=True)
+    assert re.search(r"sass_tune: 0 DFMA retuned", r2.stdout), r2.stdout
