@@ -354,6 +354,16 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     gp = gp_n; yp = yp_n; jm = jm_n;
 }
 
+// RG_SUBPIECES > 1 (experiment for the elastic-helper plan): a piece is summed as RG_SUBPIECES
+// sub-pieces of equal entry count, each from zero, added in order into the piece's running total (registers) while
+// the load pipeline of the stream runs on.  The partial sums then no longer depend on how many warps (or CTAs) share
+// a piece.  (Combining every sub-piece into `out` in (rank, sub-piece) order instead serialises the pieces of a box:
+// measured +42 % / +84 % bracket time with 2 / 4 sub-pieces.)  Measured with the total in registers: +4.8 % kernel
+// time for 2 and for 4 sub-pieces alike (the hot loops' register allocation, not the additions at the marks).  The
+// default build (RG_SUBPIECES = 1) has no marks and compiles to the SASS it always had.
+#ifndef RG_SUBPIECES
+#define RG_SUBPIECES 1
+#endif
 template <int J, bool BIG>
 __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, int e_end, double (&acc)[J + 1]) {
     typedef RecGeom<J> R;
@@ -398,6 +408,15 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     // dispatch chain per entry.  The outer loop only repeats if a list were not sorted.
     int i = e_begin;
     const int last = e_end - 1;
+#if RG_SUBPIECES > 1
+    const int e_all = e_end;
+    double tot[J + 1];
+#pragma unroll
+    for (int j = 0; j <= J; ++j) tot[j] = 0.0;
+#pragma unroll 1
+    for (int sub = 0; sub < RG_SUBPIECES; ++sub) {
+    e_end = e_begin + ((e_all - e_begin) * (sub + 1)) / RG_SUBPIECES;
+#endif
 #pragma unroll 1
     while (i < e_end) {
 #pragma unroll 1
@@ -425,6 +444,18 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
             wn = wnn; ++i;
         }
     }
+#if RG_SUBPIECES > 1
+    // mark: the sub-piece's sum joins the piece's running total (a fixed two-level tree: sub-pieces in order inside
+    // a piece, pieces in rank order inside a box); the stream's loads run on
+    if (sub + 1 < RG_SUBPIECES) {
+#pragma unroll
+        for (int j = 0; j <= J; ++j) { tot[j] += acc[j]; acc[j] = 0.0; }
+    } else {
+#pragma unroll
+        for (int j = 0; j <= J; ++j) acc[j] = tot[j] + acc[j];
+    }
+    }
+#endif
 }
 
 // out[nu][j] = conv(dA y, Omega g) - conv(Omega y, dA g)  (G, Y in shared memory).  Ends with a barrier.
