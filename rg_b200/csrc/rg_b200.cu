@@ -549,6 +549,9 @@ static size_t smem_bytes(const rgplan::Geometry& g, int n_support, bool big) {
     b += (size_t)g.M * g.JP * 8;
     b += 64 * 8 + 16;            // reduction scratch + work ticket
     b += RG_CTL_UNITS * 16;      // the convolution's control block
+#if defined(RG_SUBTOT_SMEM) && RG_SUBPIECES > 1
+    b += (size_t)12 * g.JP * 32 * 8;   // experiment: per-warp strips of the piece totals behind `out`
+#endif
     return b;
 }
 

@@ -359,7 +359,9 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
 // the load pipeline of the stream runs on.  The partial sums then no longer depend on how many warps (or CTAs) share
 // a piece.  (Combining every sub-piece into `out` in (rank, sub-piece) order instead serialises the pieces of a box:
 // measured +42 % / +84 % bracket time with 2 / 4 sub-pieces.)  Measured with the total in registers: +4.8 % kernel
-// time for 2 and for 4 sub-pieces alike (the hot loops' register allocation, not the additions at the marks).  The
+// time for 2 and for 4 sub-pieces alike (the hot loops' register allocation, not the additions at the marks); with
+// the total in spare shared memory (-DRG_SUBTOT_SMEM) +6.6 % / +9.2 %.  Conclusion: helpers should take
+// whole pieces, which costs a lone CTA nothing.  The
 // default build (RG_SUBPIECES = 1) has no marks and compiles to the SASS it always had.
 #ifndef RG_SUBPIECES
 #define RG_SUBPIECES 1
@@ -410,9 +412,13 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     const int last = e_end - 1;
 #if RG_SUBPIECES > 1
     const int e_all = e_end;
+#ifdef RG_SUBTOT_SMEM
+    double* const totp = sm.out + (size_t)P.M * (J + 1) + (size_t)(threadIdx.x >> 5) * (J + 1) * 32 + lane;
+#else
     double tot[J + 1];
 #pragma unroll
     for (int j = 0; j <= J; ++j) tot[j] = 0.0;
+#endif
 #pragma unroll 1
     for (int sub = 0; sub < RG_SUBPIECES; ++sub) {
     e_end = e_begin + ((e_all - e_begin) * (sub + 1)) / RG_SUBPIECES;
@@ -447,6 +453,18 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
 #if RG_SUBPIECES > 1
     // mark: the sub-piece's sum joins the piece's running total (a fixed two-level tree: sub-pieces in order inside
     // a piece, pieces in rank order inside a box); the stream's loads run on
+#ifdef RG_SUBTOT_SMEM   // the total lives in the warp's private strip of shared memory behind `out` ([j][lane], conflict free)
+    if (sub == 0 && RG_SUBPIECES > 1) {
+#pragma unroll
+        for (int j = 0; j <= J; ++j) { totp[j * 32] = acc[j]; acc[j] = 0.0; }
+    } else if (sub + 1 < RG_SUBPIECES) {
+#pragma unroll
+        for (int j = 0; j <= J; ++j) { totp[j * 32] += acc[j]; acc[j] = 0.0; }
+    } else {
+#pragma unroll
+        for (int j = 0; j <= J; ++j) acc[j] = totp[j * 32] + acc[j];
+    }
+#else
     if (sub + 1 < RG_SUBPIECES) {
 #pragma unroll
         for (int j = 0; j <= J; ++j) { tot[j] += acc[j]; acc[j] = 0.0; }
@@ -454,6 +472,7 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
 #pragma unroll
         for (int j = 0; j <= J; ++j) acc[j] = tot[j] + acc[j];
     }
+#endif
     }
 #endif
 }
