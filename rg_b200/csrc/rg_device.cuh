@@ -360,8 +360,8 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
 // a piece.  (Combining every sub-piece into `out` in (rank, sub-piece) order instead serialises the pieces of a box:
 // measured +42 % / +84 % bracket time with 2 / 4 sub-pieces.)  Measured with the total in registers: +4.8 % kernel
 // time for 2 and for 4 sub-pieces alike (the hot loops' register allocation, not the additions at the marks); with
-// the total in spare shared memory (-DRG_SUBTOT_SMEM) +6.6 % / +9.2 %.  Conclusion: helpers should take
-// whole pieces, which costs a lone CTA nothing.  The
+// the total in spare shared memory (-DRG_SUBTOT_SMEM) +6.6 % / +9.2 %.  DESIGN.md section 9 weighs this against
+// coarser units.  The
 // default build (RG_SUBPIECES = 1) has no marks and compiles to the SASS it always had.
 #ifndef RG_SUBPIECES
 #define RG_SUBPIECES 1
