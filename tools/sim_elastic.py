@@ -8,7 +8,7 @@ import numpy as np
 W = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "work_map_r01_expm_onestep_256.npz"))["work"].astype(np.int64)
 w=W
 US=65.0e-6; OVER=30
-SPEED = {1: 1.0, 2: 1.6, 4: 2.0}   # per-Hamiltonian speed-up with 2 / 4 CTAs (piece-granularity teams); the cluster mode measured 1.44 / 1.87
+SPEED = {1: 1.0, 2: 1.75, 4: 2.2}   # per-Hamiltonian speed-up with 2 / 4 CTAs: bracket x1.90 / x2.56 (plan for 24 virtual warps, tools/sim_team.py), 9.5 % of a Lie step on the owner alone; the cluster mode measured 1.44 / 1.87
 def sim(ws, nsm=148, elastic=True, dt=2e-3):
     ws=[(x+OVER)*US for x in ws]
     q=0; t=0.0
