@@ -1183,7 +1183,12 @@ extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_
     if (dim < 1 || dim > 3 || J < 1 || J > 15 || L < 1) return fail(-2, "bad geometry");
     rgplan::Geometry g; g.init(dim, L, J);
     std::vector<uint16_t> mask = masks_from_iminus(g, iminus_wrapped);
-    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, rg_warps_for(g.M, g.J, needs_global_records(g, mask, RG_SMEM_OPTIN)));
+    int nw_plan = rg_warps_for(g.M, g.J, needs_global_records(g, mask, RG_SMEM_OPTIN));
+    // RG_B200_VWARPS = 2..4: the plan for that many virtual warps per real warp (elastic helpers);
+    // this debug entry point only -- the kernels run the plan for the real warps
+    const char* vw = getenv("RG_B200_VWARPS");
+    if (vw && atoi(vw) >= 2 && atoi(vw) <= 4) nw_plan *= atoi(vw);
+    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, nw_plan);
     if (s.n_warps < 0) return fail(-5, "too many output modes for one CTA's convolution schedule");
     *n_warps = s.n_warps; *n_boxes = s.n_boxes; *n_entries = (int)s.entries.size() / 2; *n_support = s.n_support;
     if (cost) { cost[0] = s.fma_useful; cost[1] = s.fma_executed; cost[2] = s.cost_max; cost[3] = s.cost_total; }
