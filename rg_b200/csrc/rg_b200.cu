@@ -602,7 +602,10 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     }
     const int n_warps = rg_warps_for(g.M, g.J, big);
     for (int ci = 0; ci < 3; ++ci) {
-        const int vw = n_warps << ci;   // virtual warps of a cluster of 1, 2, 4 CTAs
+        int vw = n_warps << ci;   // virtual warps of a cluster of 1, 2, 4 CTAs
+#if RG_VWARPS > 1
+        if (ci == 0) vw *= RG_VWARPS;   // experiment: finer pieces for the one-CTA plans (rg_device.cuh, conv_all)
+#endif
         p->hs[3 * ci + 0] = rgplan::make_schedule(g, mask, false, false, vw, 1 << ci);
         p->hs[3 * ci + 1] = rgplan::make_schedule(g, mask, true, false, vw, 1 << ci);
         p->hs[3 * ci + 2] = rgplan::make_schedule(g, mask, false, true, vw, 1 << ci);
@@ -610,7 +613,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     p->sm_count = prop.multiProcessorCount;
     p->threads = n_warps * 32;
     for (int s = 0; s < 9; ++s)
-        if (p->hs[s].n_warps != (n_warps << (s / 3)) || p->hs[s].n_boxes > RG_MAX_BOXES) {
+        if (p->hs[s].n_warps != (n_warps << (s / 3)) * ((RG_VWARPS > 1 && s < 3) ? RG_VWARPS : 1) || p->hs[s].n_boxes > RG_MAX_BOXES) {
             delete p;
             return fail(-5, "too many output modes for one CTA's convolution schedule");
         }

@@ -515,12 +515,33 @@ __device__ RG_CONV_ATTR void conv_all(Ctx& c) {
     __syncthreads();
     double acc[JP];
     const long long t_stage = clock64();
+    // RG_VWARPS > 1 (experiment for the elastic-helper plan; compiled out by default): the plan is
+    // dealt to RG_VWARPS virtual warps per real warp -- finer pieces, the unit a helper CTA would take -- and a lone CTA
+    // runs them in rounds, virtual warp vv * (warps of the CTA) + w in round vv.  Interleaved, not blocked: a piece of
+    // rank r waits for the piece of rank r - 1, which belongs to the previous virtual warp, and that one must be running
+    // concurrently or be finished (with blocked rounds every warp would wait for its neighbour's second round).
+#ifndef RG_VWARPS
+#define RG_VWARPS 1
+#endif
+#if RG_VWARPS > 1
+    const int nvirt = max(1, S.n_warps / (nwc * c.csize));
+    if (vw < nwc * c.csize) {
+#else
     if (vw < S.n_warps) {
+#endif
         for (int st = 0; st < S.n_stages; ++st) {
             const int4* pieces = S.pieces + (size_t)st * S.n_warps * S.maxp;
+#if RG_VWARPS > 1
+#pragma unroll 1
+            for (int vv = 0; vv < nvirt; ++vv) {
+            const int pw = c.crank * nwc * nvirt + vv * nwc + w;
+#else
+            {
+            const int pw = vw;
+#endif
 #pragma unroll 1
             for (int q = 0; q < S.maxp; ++q) {
-                const int4 p = pieces[vw * S.maxp + q];      // heads first, the continuation (if any) last
+                const int4 p = pieces[pw * S.maxp + q];      // heads first, the continuation (if any) last
                 if (p.x < 0) continue;
                 conv_piece<J, BIG>(c, p.x, p.y, p.z, acc);
                 if (lane == 0) {
@@ -545,6 +566,7 @@ __device__ RG_CONV_ATTR void conv_all(Ctx& c) {
                     vctl[p.x] = p.w + 1;
                     if (st == 0) atomicAdd(&ctl[nb_all], 1);
                 }
+            }
             }
         }
     }
