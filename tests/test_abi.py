@@ -325,3 +325,45 @@ def test_schedule_replay_with_virtual_warps(vwarps, monkeypatch):
     keep[:(c.M + 1) // 2] = True
     keep = np.roll(keep.reshape(c.dim * (2 * c.L + 1,)), c.dim * (-c.L,), axis=tuple(range(c.dim)))
     assert relmax(got * keep, want * keep) < 1e-13
+
+
+@pytest.mark.parametrize("dim,L,J", [(1, 3, 2), (1, 20, 4), (2, 2, 3), (2, 4, 6), (2, 6, 5), (2, 9, 4), (3, 2, 2), (3, 3, 4)])
+def test_plans_of_random_supports_cover_every_pair_once(dim, L, J):
+    """Planner invariants on geometries and I^- supports it was not tuned for (random supports, partial last boxes of
+    every size): in every stage the lanes are a permutation of the output modes, and every (output mode, source mode)
+    pair whose difference lies in the grid is visited exactly once over both stages."""
+    rng = np.random.default_rng(1000 * dim + 10 * L + J)
+    n1, M = 2 * L + 1, (2 * L + 1) ** dim
+
+    class C:            # the attributes fetch_schedule reads
+        pass
+    c = C()
+    c.dim, c.L, c.J = dim, L, J
+    c.Iminus = rng.random((J + 1,) + dim * (n1,)) < 0.4
+    c.Iminus[..., :] |= rng.random(c.Iminus.shape) < 0.05
+    strides = [n1 ** (dim - 1 - d) for d in range(dim)]
+    coords = np.stack([(np.arange(M) // strides[d]) % n1 for d in range(dim)], axis=1)
+    for mode in (0, 2):
+        s = fetch_schedule(c, mode)
+        nout = M if mode == 0 else (M + 1) // 2
+        nb1 = s["nb"] // s["nst"]
+        for st in range(s["nst"]):
+            lanes = s["lane_out"][st * nb1 * 32:(st + 1) * nb1 * 32]
+            assert sorted(lanes[lanes >= 0]) == list(range(nout)), (mode, st)
+        supp = np.nonzero(s["supp"] >= 0)[0]
+        visits = np.zeros((nout, M), dtype=int)
+        for box, b, e, rank in s["pieces"]:
+            if box < 0:
+                continue
+            lanes = s["lane_out"][box * 32:(box + 1) * 32]
+            lanes = lanes[lanes >= 0]
+            nu1 = (s["entries"][b:e, 1] & 0xffff).astype(int)
+            u = coords[lanes][:, None, :] - coords[nu1][None, :, :] + L
+            ok = ((u >= 0) & (u <= 2 * L)).all(axis=2)
+            for li, nu in enumerate(lanes):
+                visits[nu, nu1[ok[li]]] += 1
+        u = coords[:nout][:, None, :] - coords[supp][None, :, :] + L
+        need = ((u >= 0) & (u <= 2 * L)).all(axis=2)
+        want = np.zeros((nout, M), dtype=int)
+        want[:, supp] = need
+        assert (visits == want).all(), (mode, int(np.abs(visits - want).sum()))
