@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--nxy", type=int, default=GRID["Nxy"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-ct", action="store_true", help="skip the expm_multiply / expm_adapt side measurements")
-    ap.add_argument("--cpu-sample", type=int, default=8, help="side of the strided CPU-baseline subsample")
+    ap.add_argument("--port", action="store_true", help="reference arm: time the C port (oracle/rg_oracle.c) instead of the reference files")
+    ap.add_argument("--dump-map", type=int, default=0, help="reference arm: add the sample's (conv, count, error) map to the JSON line")
     ap.add_argument("--neighbour-queue", action="store_true", help="experimental: heavy points queue their grid neighbours")
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="diagnostic: run rank 0's shard of an N-rank job on one GPU (tail / load-balance study)")
@@ -88,48 +89,140 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def cpu_sample_points(nxy, side):
-    """Strided subsample of the Nxy grid: ix,iy in {s + s/2*.., ...}; side=8 at Nxy=256 -> {24,56,...,248}."""
-    stride = nxy // side
-    off = stride - stride // 4
-    xs = np.linspace(GRID["AmpInf"][0], GRID["AmpSup"][0], nxy)[off::stride]
-    ys = np.linspace(GRID["AmpInf"][1], GRID["AmpSup"][1], nxy)[off::stride]
-    return xs, ys, "%dx%d strided subsample (ix,iy in {%d,%d,...}) of the Nxy=%d grid" % (len(xs), len(ys), off, off + stride, nxy)
+# The reference's own CPU path (RG_modules.point -> RG.converge -> ... -> scipy.signal.convolve, RG_modules.py:121-143):
+# the UNMODIFIED reference files, copied by __graft_entry__.build() into the git-ignored oracle/_ref/ so that they
+# travel to the GPU box, loaded through oracle/ref_loader.py (matplotlib stub + CWD holding theta_taylor.mat) and
+# fanned out over a process pool like RG_modules.compute_region does (one task per point, chunksize 1, stock order).
+SUB16 = 16   # the 16x16 strided subsample ix, iy in {8, 24, ..., 248} of the Nxy=256 grid
 
 
-def run_cpu(ct, nxy, side, steps, warmup):
+def sub16_points(nxy):
+    stride = nxy // SUB16
+    idx = np.arange(stride // 2, nxy, stride)
+    xs = np.linspace(GRID["AmpInf"][0], GRID["AmpSup"][0], nxy)[idx]
+    ys = np.linspace(GRID["AmpInf"][1], GRID["AmpSup"][1], nxy)[idx]
+    pts = [(float(x), float(y)) for y in ys for x in xs]          # y is the outer loop (RG_modules.py:138-139)
+    flat = np.array([iy * nxy + ix for iy in idx for ix in idx])
+    return pts, flat, "16x16 strided subsample (ix,iy in {%d,%d,...,%d}) of the Nxy=%d grid" % (idx[0], idx[1], idx[-1], nxy)
+
+
+def reference_dir():
+    d = os.path.join(ROOT, "oracle", "_ref")
+    return d if os.path.isfile(os.path.join(d, "RG.py")) and os.path.isfile(os.path.join(d, "theta_taylor.mat")) else None
+
+
+_REF = {}
+
+
+def _ref_init(ct, refdir):
+    """Pool worker: build the reference's RG object once (np.random.seed(12345) per worker)."""
+    import warnings
+    warnings.simplefilter("ignore")
+    os.environ["RG_REFERENCE_DIR"] = refdir
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    ref_loader.REFERENCE_DIR = refdir
+    RG, RG_modules, RG_dict = ref_loader.load()
+    np.random.seed(12345)
+    prm = ref_loader.make_params(L=GRID["L"], J=GRID["J"], CT=ct, AmpInf=[float(v) for v in GRID["AmpInf"]],
+                                 AmpSup=[float(v) for v in GRID["AmpSup"]], Nxy=GRID["Nxy"])
+    _REF["case"] = RG.RG(prm)
+    _REF["point"] = RG_modules.point
+
+
+def _ref_point(xy):
+    t0 = time.perf_counter()
+    (conv, count), err = _REF["point"](xy[0], xy[1], _REF["case"])
+    return int(conv), int(count), int(err), time.perf_counter() - t0
+
+
+def _port_init(ct, _unused):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import rg_oracle as ro
-    cores = ro._lib().oracle_max_threads()
-    orc = ro.OracleRG(ro.default_params(L=GRID["L"], J=GRID["J"], CT=ct))
-    xs, ys, desc = cpu_sample_points(nxy, side)
-    n = len(xs) * len(ys)
-    for _ in range(warmup):
-        orc.region(xs[:2], ys[:2], nthreads=cores)      # warm the pool; a bounded sample pass is the step
+    _REF["orc"] = ro.OracleRG(ro.default_params(L=GRID["L"], J=GRID["J"], CT=ct))
+
+
+def _port_point(xy):
     t0 = time.perf_counter()
-    nl = 0
-    for _ in range(steps):
-        conv, count, err, liou = orc.region(xs, ys, nthreads=cores)
-        nl += int(liou.sum())
-    dt = time.perf_counter() - t0
-    return dict(value=steps * n / dt, unit="points/s", cores=cores, kind="port",
-                sample=desc + "; oracle/rg_oracle.c (direct-convolution port of the reference's numpy/scipy path), "
-                "OpenMP over points, %d liouville evaluations in %.1f s" % (nl, dt)), dt / steps, n
+    conv, count, err, _ = _REF["orc"].points([xy], nthreads=1)
+    return int(conv[0]), int(count[0]), int(err[0]), time.perf_counter() - t0
+
+
+def run_reference(ct, nxy, steps, warmup, kind=None):
+    """K timed steps: the sample's points in stock order, cut into K contiguous chunks (step s = chunk s), streamed
+    through ONE pool.imap(chunksize=1) -- no barrier between steps, as on the full grid where a row of 256 points
+    keeps every core busy.  Returns the JSON fields of the run."""
+    import multiprocessing as mp
+    refdir = reference_dir()
+    if kind is None:
+        kind = "reference" if refdir else "port"
+    cores = len(os.sched_getaffinity(0))          # never from OpenMP: torchrun exports OMP_NUM_THREADS=1
+    pts, flat, desc = sub16_points(nxy)
+    lim = int(os.environ.get("RG_BENCH_REF_LIMIT", "0"))      # smoke tests of this script only
+    if lim > 0:
+        pts, flat, desc = pts[-lim:], flat[-lim:], desc + " [last %d points only]" % lim
+    init, fn = (_ref_init, _ref_point) if kind == "reference" else (_port_init, _port_point)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=init, initargs=(ct, refdir)) as pool:
+        for _ in range(max(1, warmup)):           # warm-up step: one cheap point (diverges in one rg_map) per worker
+            pool.map(fn, [pts[-1]] * cores, chunksize=1)
+        bounds = np.linspace(0, len(pts), steps + 1).round().astype(int)
+        t0 = time.perf_counter()
+        res, step_end = [], []
+        for i, r in enumerate(pool.imap(fn, pts, chunksize=1)):
+            res.append(r)
+            while len(step_end) < steps and i + 1 >= bounds[len(step_end) + 1]:
+                step_end.append(time.perf_counter() - t0)
+        wall = time.perf_counter() - t0
+    res = np.array(res, dtype=np.float64)
+    core_s = float(res[:, 3].sum())
+    out = dict(value=len(pts) / wall, unit="points/s", cores=cores, kind=kind, wall_s=wall,
+               core_seconds_per_point=core_s / len(pts), slowest_point_s=float(res[:, 3].max()),
+               balanced_points_per_s=cores * len(pts) / core_s,
+               extrapolated_full_grid_hours=(nxy * nxy / (len(pts) / wall)) / 3600.0,
+               sample=desc + ", %s, every point once over the %d step(s); " % (ct, steps) +
+               ("the unmodified reference (oracle/_ref: RG.py, RG_modules.py point(), scipy FFT convolution)" if kind == "reference"
+                else "oracle/rg_oracle.c (direct-convolution C port; the reference files are absent)") +
+               ", fork pool of %d processes (os.sched_getaffinity), imap chunksize=1, stock order; %.1f core-s in %.1f s wall"
+               % (cores, core_s, wall))
+    gpath = os.path.join(ROOT, "tests", "golden", "region_L10J10_sub16_%s.npz" % ct)
+    if nxy == GRID["Nxy"] and os.path.exists(gpath) and lim <= 0:
+        g = np.load(gpath)
+        ok = (np.array_equal(res[:, 0].reshape(16, 16), g["conv"]) and np.array_equal(res[:, 1].reshape(16, 16), g["count"])
+              and np.array_equal(res[:, 2].reshape(16, 16), g["error"]))
+        out["matches_frozen_golden"] = bool(ok)
+    return out, res[:, :3].astype(np.int64), flat, wall / steps
 
 
 def main_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cb, ms, n = run_cpu(a.ct, a.nxy, a.cpu_sample, a.steps, min(a.warmup, 1))
+    cb, smap, flat, per_step = run_reference(a.ct, a.nxy, a.steps, a.warmup, kind=("port" if a.port else None))
     line = {"impl": "reference", "metric": "region grid points/sec (Nxy=%d, L=J=10)" % a.nxy, "value": cb["value"],
-            "unit": "points/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms * 1e3,
+            "unit": "points/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": per_step * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "region Nxy=%d L=J=10 golden-mean torus, %s; each step = %s" % (a.nxy, a.ct, cb["sample"])},
+            "config": {"workload": "region Nxy=%d, L=J=10, golden-mean torus N=[[1,1],[1,0]], K=((0,1,0),(0,1,1)), AmpSup=[0.12,0.35], "
+                                   "TolMin=1e-10, TolMax=1e4, MaxLie=5000, NormChoice=sum, %s; bounded sample: %s" % (a.nxy, a.ct, cb["sample"]),
+                       "canonical_transformation": a.ct},
             "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    if a.dump_map:
+        line["sample_map"] = {"flat_index": flat.tolist(), "conv_count_error": smap.tolist()}
     print(json.dumps(line))
+
+
+def cpu_baseline_subprocess(ct, nxy):
+    """The reference arm in a child process (this one holds a CUDA context; the pool forks).  Returns its JSON line."""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--ct", ct, "--nxy", str(nxy), "--dump-map", "1"], capture_output=True, text=True,
+                       env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+    for ln in r.stdout.splitlines()[::-1]:
+        if ln.startswith("{"):
+            return json.loads(ln)
+    raise RuntimeError("reference arm failed: " + r.stderr[-2000:])
 
 
 # ---------------------------------------------------------------------------------------------- our arm
@@ -291,9 +384,20 @@ def main_b200(a):
             "result_checksum": {"converged": int(full[:, 0].sum()), "count_sum": int(full[:, 1].sum()),
                                 "errors": {str(k): int(v) for k, v in zip(*np.unique(full[:, 2], return_counts=True))}},
         }
-        if world == 1 and not a.no_cpu_baseline:
-            cb, _, _ = run_cpu(a.ct, a.nxy, a.cpu_sample, 1, 0)
-            line["cpu_baseline"] = cb
+        if world == 1 and not a.no_cpu_baseline and a.emulate_world <= 1:
+            # the reference's CPU path on this box's host cores, same run, and the parity gate of
+            # the GPU map restricted to the sample must equal the CPU map bit for bit
+            ref = cpu_baseline_subprocess(a.ct, a.nxy)
+            line["cpu_baseline"] = ref["cpu_baseline"]
+            sm = ref.get("sample_map")
+            if sm:
+                cpu_map = np.array(sm["conv_count_error"], dtype=np.int64)
+                gpu_map = full[np.array(sm["flat_index"])].astype(np.int64)
+                bad = np.flatnonzero((cpu_map != gpu_map).any(axis=1))
+                line["parity_gate"] = {"points": int(len(cpu_map)), "mismatches": int(len(bad)),
+                                       "mismatching_flat_indices": [int(sm["flat_index"][b]) for b in bad],
+                                       "what": "(conv, count, error) of the GPU map at the CPU sample's points vs the "
+                                               "%s arm of this run" % ref["cpu_baseline"]["kind"]}
         if world == 1 and not a.no_other_ct:
             line["other_transformations"] = other_transformations(a, local)
         sys.stdout.flush()

@@ -11,7 +11,10 @@
  *    rg_last_error() returns a thread-local message for the last non-zero return.
  *  - no exceptions or callbacks cross the ABI; the caller owns every buffer it passes.
  *  - array arguments may be HOST or DEVICE pointers (detected with cudaPointerGetAttributes);
- *    host buffers are staged through pinned memory inside the call.
+ *    host buffers are copied with cudaMemcpyAsync on the plan's stream into a grow-only device arena the
+ *    plan owns (no cudaMalloc/cudaFree per call in the steady state; pinned host buffers make the copies
+ *    truly asynchronous).  Device-resident inputs written on another stream must be synchronised by the
+ *    caller before the call; every call returns after its own stream has drained.
  *  - Hamiltonian coefficient arrays use the reference layout: f[j][nu_1]...[nu_n], C-contiguous
  *    float64, nu_i in wrapped order 0..L,-L..-1 (RG.py:61,66-67); a batch is B such arrays
  *    back to back.  vecjl = (J+1)*(2L+1)^dim, M = (2L+1)^dim.
@@ -160,9 +163,17 @@ int rg_sym(rg_plan* plan, int32_t n, const double* f, double* out);
 /* N-matrix re-indexing + rescaling, the head of RG.rg_map (RG.py:210-216). */
 int rg_reindex_rescale(rg_plan* plan, const rg_tables* tab, int32_t n, const double* f, const int32_t* k0, double* out);
 
-/* RG.compute_m_s (RG.py:130-150): (m*, s) per Hamiltonian for caller-supplied y. */
+/* RG.compute_m_s(y, n0, tol, ell) (RG.py:130-150): (m*, s) per Hamiltonian for caller-supplied y; n0 and ell enter the
+   test of RG.py:135 (the reference's defaults are n0 = 1, ell = 2; `tol` is unused there too).  norm1 (optional)
+   receives the 1-norm estimate of L_y the selection started from. */
 int rg_compute_m_s(rg_plan* plan, int32_t n, const double* y0, const double* y1, const double* y2,
-                   const double* Omega_nu, int32_t* m_star, int32_t* scale, double* norm1);
+                   const double* Omega_nu, double n0, double ell, int32_t* m_star, int32_t* scale, double* norm1);
+
+/* RG.pnorm(y, p) (RG.py:119-123): onenormest((L_y)^p)^(1/p) per Hamiltonian, out[n]; the block 1-norm estimator is
+   scipy.sparse.linalg.onenormest restated (Higham-Tisseur Alg. 2.4, t = 2, itmax = 5) with the reference's
+   rmatvec = -matvec. */
+int rg_pnorm(rg_plan* plan, int32_t n, const double* y0, const double* y1, const double* y2,
+             const double* Omega_nu, int32_t p, double* out);
 
 /* Host-only introspection of the convolution schedule (no device needed): used by tests to replay the
    schedule in numpy.  mode: 0 = I^- support, all output modes; 1 = dense (caller-supplied y); 2 = I^-

@@ -62,7 +62,8 @@ SIGNATURES = {
     "rg_norm": (ctypes.c_int, [vp, ctypes.c_int32, vp, ctypes.c_int32, vp]),
     "rg_sym": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp]),
     "rg_reindex_rescale": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, vp]),
-    "rg_compute_m_s": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp, vp, vp, vp]),
+    "rg_compute_m_s": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp, ctypes.c_double, ctypes.c_double, vp, vp, vp]),
+    "rg_pnorm": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, vp, vp, ctypes.c_int32, vp]),
     "rg_debug_schedule": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, ctypes.c_int32,
                                          c_int_p, c_int_p, ctypes.POINTER(c_int_p), ctypes.POINTER(c_int_p), c_int_p,
                                          ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), c_int_p,

@@ -74,6 +74,7 @@ struct Job {
     double* f_out; double* y0_out; double* y1_out; double* y2_out; double* y3_out;
     long long* n_liou; long long* n_lie; long long* n_maps;
     int* m_out; int* s_out; double* norm1_out;   // mode 6
+    int pnorm_p; double ms_n0, ms_ell;            // mode 6: pnorm_p > 0 -> RG.pnorm(y, p) only; else compute_m_s(y, n0, ell)
     long long* liou_out;                          // optional per-item liouville count
     // heavy-neighbour scheduling (region grids): a point that turns out heavy queues its grid neighbours
     int* claimed; int* prio_q; int* q_ctr; int row_len; int hot_threshold; int q_cap;
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
         }
         const int item = *sh_item;
         if (item >= job.n) break;
-        c.n_liou = 0; c.n_lie = 0; c.symm = 0; c.t_conv = 0; c.t_epi = 0; c.t_busy = 0;
+        c.n_liou = 0; c.n_lie = 0; c.budget_base = 0; c.symm = 0; c.t_conv = 0; c.t_epi = 0; c.t_busy = 0;
         const long long t_item = clock64();
         c.rng = 0x243F6A8885A308D3ull ^ ((uint64_t)(item + 1) * 0x9E3779B97F4A7C15ull);
         long long n_maps = 0;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
             bool overflow = false, budget = false, hot = false;
             while (P.tol_max > ni && ni > P.tol_min) {
                 if (k0 + k >= T.n_tab) { overflow = true; break; }
-                if (c.n_liou > P.max_liouville) { budget = true; break; }
+                if (c.n_liou - c.budget_base > P.max_liouville) { budget = true; break; }
                 f = rg_map_dev<J, BIG>(c, f, T, k0 + k, err, ni);
                 ++k; ++n_maps;
                 if (job.row_len > 0 && !hot && c.n_liou > job.hot_threshold) {
@@ -261,8 +262,13 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
             __syncthreads();
             build_Y<J, BIG>(c, 1.0, 1.0, false);
             __syncthreads();
-            int m_star; double scale, n1;
-            compute_m_s<J, BIG>(c, job.y0[item], m_star, scale, n1);
+            int m_star = 0; double scale = 0.0, n1;
+            if (job.pnorm_p > 0) {   // RG.pnorm(y, p)  RG.py:119-123
+                const double e = onenormest_pow<J, BIG>(c, job.y0[item], job.pnorm_p);
+                n1 = job.pnorm_p == 1 ? e : pow(e, 1.0 / (double)job.pnorm_p);
+            } else {
+                compute_m_s<J, BIG>(c, job.y0[item], m_star, scale, n1, job.ms_n0, job.ms_ell);
+            }
             if (threadIdx.x == 0) {
                 job.m_out[item] = m_star;
                 job.s_out[item] = scale < 2147483647.0 ? (int)scale : 2147483647;
@@ -490,9 +496,40 @@ struct rg_plan {
     std::vector<void*> owned;  // device allocations
     std::vector<int> w2c;      // wrapped -> centred
     void* kernel = nullptr;
-    // scratch for staging
-    std::vector<void*> scratch;
+    // staging arena: device memory for host-side arguments of an ABI call.  Grow-only; a call bumps through it, the
+    // next call starts from the top again (calls are synchronous), so the steady state has no cudaMalloc/cudaFree.
+    std::vector<std::pair<char*, size_t>> arena;   // chunks (more than one only until the next call consolidates them)
+    size_t arena_used = 0;                          // bytes taken from the last chunk
+    size_t arena_want = 0;                          // bytes requested by the current call (all chunks)
 };
+
+static int arena_reset(rg_plan* p) {
+    if (p->arena.size() > 1 || (p->arena.size() == 1 && p->arena_want > p->arena[0].second)) {
+        size_t cap = 0;
+        for (auto& c : p->arena) { cap += c.second; cudaFree(c.first); }
+        p->arena.clear();
+        cap = std::max(cap, p->arena_want);
+        char* d = nullptr;
+        CU(cudaMalloc(&d, cap));
+        p->arena.push_back({d, cap});
+    }
+    p->arena_used = 0; p->arena_want = 0;
+    return 0;
+}
+static int arena_alloc(rg_plan* p, size_t bytes, void** out) {
+    bytes = (std::max<size_t>(bytes, 8) + 255) & ~(size_t)255;
+    p->arena_want += bytes;
+    if (p->arena.empty() || p->arena_used + bytes > p->arena.back().second) {
+        const size_t cap = std::max<size_t>(bytes, std::max<size_t>((size_t)1 << 20, p->arena.empty() ? 0 : 2 * p->arena.back().second));
+        char* d = nullptr;
+        CU(cudaMalloc(&d, cap));
+        p->arena.push_back({d, cap});
+        p->arena_used = 0;
+    }
+    *out = p->arena.back().first + p->arena_used;
+    p->arena_used += bytes;
+    return 0;
+}
 
 struct rg_tables {
     rg_plan* plan;
@@ -581,7 +618,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     if (prm->dim < 1 || prm->dim > 3) return fail(-2, "dim must be 1, 2 or 3");
     if (prm->J < 2 || prm->J > 15) return fail(-2, "J must be in 2..15");
     if (prm->L < 1 || prm->L > 60) return fail(-2, "L must be in 1..60");
-    if (!pick_kernel(prm->J, false)) return fail(-3, "no kernel compiled for J=" + std::to_string(prm->J) + " (rebuild with RG_B200_J_LIST)");
+    if (!pick_kernel(prm->J, false)) return fail(-3, "no kernel compiled for J=" + std::to_string(prm->J) + " (rebuild with -DRG_J_LIST)");
     if (prm->ct < 0 || prm->ct > 2) return fail(-2, "unknown canonical transformation");
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -748,6 +785,9 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     // conv_kernel needs 2*vecjl doubles of dynamic shared memory
     if ((size_t)2 * g.vecjl * 8 <= (size_t)prop.sharedMemPerBlockOptin)
         CU(cudaFuncSetAttribute(conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * g.vecjl * 8));
+    // the uploads and the memset above went through the legacy default stream; the kernels run on p->stream
+    // (non-blocking): order them once, here
+    CU(cudaDeviceSynchronize());
     *out = p;
     return 0;
 }
@@ -756,6 +796,7 @@ extern "C" int rg_plan_destroy(rg_plan* p) {
     if (!p) return 0;
     cudaSetDevice(p->device);
     for (void* d : p->owned) cudaFree(d);
+    for (auto& c : p->arena) cudaFree(c.first);
     if (p->ws) cudaFree(p->ws);
     if (p->ticket) cudaFree(p->ticket);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -794,6 +835,7 @@ extern "C" int rg_tables_create(rg_plan* p, int32_t n_tab, const double* nrm_tab
     CU(cudaMemcpy(t->d_nrm, nrm_tab, sizeof(double) * n_tab, cudaMemcpyHostToDevice));
     CU(cudaMemcpy(t->d_onu, onu.data(), sizeof(double) * onu.size(), cudaMemcpyHostToDevice));
     t->t.n_tab = n_tab; t->t.nrm = t->d_nrm; t->t.Omega_nu = t->d_onu;
+    CU(cudaDeviceSynchronize());   // legacy-stream uploads before any launch on the plan's stream
     *out = t;
     return 0;
 }
@@ -816,18 +858,19 @@ static bool is_device_ptr(const void* p) {
 
 struct Stage {
     rg_plan* p;
-    std::vector<void*> tmp;
     struct Back { void* host; void* dev; size_t bytes; };
     std::vector<Back> backs;
-    explicit Stage(rg_plan* p_) : p(p_) {}
-    ~Stage() { for (void* d : tmp) cudaFree(d); }
+    int rc0;
+    explicit Stage(rg_plan* p_) : p(p_) { rc0 = arena_reset(p); }
+    // device scratch of `bytes` from the plan's arena (lives until the next ABI call on this plan)
+    int dev(size_t bytes, void** out) { if (rc0) return rc0; return arena_alloc(p, bytes, out); }
     // input: returns device pointer holding `bytes` of src
     int in(const void* src, size_t bytes, const void** out) {
         if (!src) { *out = nullptr; return 0; }
         if (is_device_ptr(src)) { *out = src; return 0; }
         void* d = nullptr;
-        CU(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
-        tmp.push_back(d);
+        int rc = dev(bytes, &d);
+        if (rc) return rc;
         CU(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, p->stream));
         *out = d;
         return 0;
@@ -837,8 +880,8 @@ struct Stage {
         if (!dst) { *out = nullptr; return 0; }
         if (is_device_ptr(dst)) { *out = dst; return 0; }
         void* d = nullptr;
-        CU(cudaMalloc(&d, std::max<size_t>(bytes, 8)));
-        tmp.push_back(d);
+        int rc = dev(bytes, &d);
+        if (rc) return rc;
         if (copy_in) CU(cudaMemcpyAsync(d, dst, bytes, cudaMemcpyHostToDevice, p->stream));
         else CU(cudaMemsetAsync(d, 0, bytes, p->stream));
         backs.push_back(Back{dst, d, bytes});
@@ -858,8 +901,7 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     const rgplan::Geometry& g = p->g;
     long long* d_cnt = nullptr;
     if (stats) {
-        CU(cudaMalloc(&d_cnt, sizeof(long long) * 7 * (size_t)std::max(job.n, 1)));
-        st.tmp.push_back(d_cnt);
+        { void* v; int rc = st.dev(sizeof(long long) * 7 * (size_t)std::max(job.n, 1), &v); if (rc) return rc; d_cnt = (long long*)v; }
         CU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 7 * (size_t)std::max(job.n, 1), p->stream));
         job.n_liou = d_cnt; job.n_lie = d_cnt + job.n; job.n_maps = d_cnt + 2 * (size_t)job.n;
     }
@@ -940,7 +982,7 @@ extern "C" int rg_region_work(rg_plan* p, const rg_tables* tab, int32_t n, const
     int rc;
     const void* d;
     int* d_kf = nullptr;
-    CU(cudaMalloc(&d_kf, sizeof(int) * nK)); st.tmp.push_back(d_kf);
+    { void* v; if ((rc = st.dev(sizeof(int) * nK, &v))) return rc; d_kf = (int*)v; }
     CU(cudaMemcpyAsync(d_kf, kf.data(), sizeof(int) * nK, cudaMemcpyHostToDevice, p->stream));
     job.K_flat = d_kf;
     if ((rc = st.in(amps, sizeof(double) * (size_t)n * nK, &d))) return rc; job.amps = (const double*)d;
@@ -953,7 +995,7 @@ extern "C" int rg_region_work(rg_plan* p, const rg_tables* tab, int32_t n, const
         // claimed[n] | q_ctr[4] | prio_q[4n], zero-initialised
         const size_t words = (size_t)n + 4 + 4 * (size_t)n;
         int* d_sched = nullptr;
-        CU(cudaMalloc(&d_sched, sizeof(int) * words)); st.tmp.push_back(d_sched);
+        { void* v; if ((rc = st.dev(sizeof(int) * words, &v))) return rc; d_sched = (int*)v; }
         CU(cudaMemsetAsync(d_sched, 0, sizeof(int) * words, p->stream));
         job.claimed = d_sched; job.q_ctr = d_sched + n; job.prio_q = d_sched + n + 4;
         job.row_len = row_len; job.hot_threshold = hot_threshold > 0 ? hot_threshold : 1500; job.q_cap = 4 * n;
@@ -1025,10 +1067,12 @@ static int stage_Omega_nu(rg_plan* p, Stage& st, const double* Omega_nu, const d
     if (is_device_ptr(Omega_nu)) CU(cudaMemcpy(h.data(), Omega_nu, sizeof(double) * M, cudaMemcpyDeviceToHost));
     else memcpy(h.data(), Omega_nu, sizeof(double) * M);
     for (int i = 0; i < M; ++i) c[i] = h[p->g.wrapped_of_centred(i)];
-    double* d = nullptr;
-    CU(cudaMalloc(&d, sizeof(double) * M)); st.tmp.push_back(d);
-    CU(cudaMemcpy(d, c.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
-    *out = d;
+    void* d = nullptr;
+    int rc = st.dev(sizeof(double) * M, &d);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(d, c.data(), sizeof(double) * M, cudaMemcpyHostToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));   // `c` is a local: the copy must have left it
+    *out = (const double*)d;
     return 0;
 }
 
@@ -1151,19 +1195,36 @@ extern "C" int rg_conv_product(rg_plan* p, int32_t n, const double* f1, const do
     if ((rc = st.in(f2, vb, &d2))) return rc;
     if ((rc = st.outp(out, vb, &o))) return rc;
     if (n > 0) {
-        conv_kernel<<<std::min(n, 148 * 2), 256, 2 * p->g.vecjl * 8, p->stream>>>(p->dp, n, (const double*)d1, (const double*)d2, (double*)o);
+        conv_kernel<<<std::min(n, p->sm_count * 2), 256, 2 * p->g.vecjl * 8, p->stream>>>(p->dp, n, (const double*)d1, (const double*)d2, (double*)o);
         CU(cudaGetLastError());
     }
     return st.finish();
 }
 
+static int m_s_job(rg_plan* p, int32_t n, const double* y0, const double* y1, const double* y2, const double* Omega_nu,
+                   int32_t pnorm_p, double n0, double ell, int32_t* m_star, int32_t* scale, double* norm1);
+
 extern "C" int rg_compute_m_s(rg_plan* p, int32_t n, const double* y0, const double* y1, const double* y2,
-                              const double* Omega_nu, int32_t* m_star, int32_t* scale, double* norm1) {
+                              const double* Omega_nu, double n0, double ell, int32_t* m_star, int32_t* scale, double* norm1) {
     if (!p || n < 0 || !y0 || !y1 || !y2 || !Omega_nu || !m_star || !scale) return fail(-1, "bad argument");
+    if (!(n0 > 0.0) || !(ell > 0.0)) return fail(-2, "n0 and ell must be positive");
+    return m_s_job(p, n, y0, y1, y2, Omega_nu, 0, n0, ell, m_star, scale, norm1);
+}
+
+extern "C" int rg_pnorm(rg_plan* p, int32_t n, const double* y0, const double* y1, const double* y2,
+                        const double* Omega_nu, int32_t power, double* out) {
+    if (!p || n < 0 || !y0 || !y1 || !y2 || !Omega_nu || !out) return fail(-1, "bad argument");
+    if (power < 1 || power > 64) return fail(-2, "pnorm: p must be in 1..64");
+    std::vector<int32_t> m((size_t)std::max(n, 1)), s((size_t)std::max(n, 1));
+    return m_s_job(p, n, y0, y1, y2, Omega_nu, power, 1.0, 2.0, m.data(), s.data(), out);
+}
+
+static int m_s_job(rg_plan* p, int32_t n, const double* y0, const double* y1, const double* y2, const double* Omega_nu,
+                   int32_t pnorm_p, double n0, double ell, int32_t* m_star, int32_t* scale, double* norm1) {
     CU(cudaSetDevice(p->device));
     Stage st(p);
     Job job; memset(&job, 0, sizeof(job));
-    job.mode = 6; job.n = n; job.sched = 1;
+    job.mode = 6; job.n = n; job.sched = 1; job.pnorm_p = pnorm_p; job.ms_n0 = n0; job.ms_ell = ell;
     const size_t vb = sizeof(double) * (size_t)n * p->g.vecjl;
     int rc; const void* d; void* o;
     if ((rc = st.in(y0, sizeof(double) * (size_t)n, &d))) return rc; job.y0 = (const double*)d;

@@ -79,6 +79,7 @@ struct Ctx {
     double2* rec; // global operand records (plans with rec_global), else unused
     const double* Omega_nu;  // current Omega.nu, centred, global
     long long n_liou, n_lie;
+    long long budget_base;   // n_liou when the current converge started: max_liouville is a budget per converge (RG.approach runs many)
     uint64_t rng;  // state of the 1-norm estimator's +-1 columns (seeded per Hamiltonian)
     long long t_conv, t_epi;  // SM clocks spent in conv_all / series_epilogue (thread 0's view; profiling aid)
     long long t_busy;         // of t_conv: clocks warp 0 spent computing its own pieces (the rest is barrier wait)
@@ -785,7 +786,7 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
         if (c1 + c2 < tol * r.y) break;
         else if (c1 + c2 > P.tol_max) { err = 1; break; }
         c1 = c2;
-        if (m >= P.max_series || c.n_liou > P.max_liouville) { err = 1; break; }  // safety: the reference would spin (quirk Q6)
+        if (m >= P.max_series || c.n_liou - c.budget_base > P.max_liouville) { err = 1; break; }  // safety: the reference would spin (quirk Q6)
     }
     c.sidx = sidx_saved;
     RG_DBG_ADD1(21);
@@ -973,7 +974,7 @@ __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, i
     f = dst;
     int err = 0, kl = 0;
     double2 nn = sym_and_norms<J>(c, f, false);
-    while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie && c.n_liou <= P.max_liouville) {
+    while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie && c.n_liou - c.budget_base <= P.max_liouville) {
         RG_DBG_T1;
         double a;
         { RG_DBG_T0; a = generate_y<J>(c, f);
@@ -1007,9 +1008,10 @@ __device__ __forceinline__ int converge_dev(Ctx& c, double*& f, const Tables& T,
     double ni = nn.y;
     int k = 0;
     err = 0; status = 0;
+    c.budget_base = c.n_liou;
     while (P.tol_max > ni && ni > P.tol_min) {
         if (k0 + k >= T.n_tab) { status = 1; break; }
-        if (c.n_liou > P.max_liouville) { status = 2; break; }
+        if (c.n_liou - c.budget_base > P.max_liouville) { status = 2; break; }
         f = rg_map_dev<J, BIG>(c, f, T, k0 + k, err, ni);
         ++k; ++n_maps;
     }

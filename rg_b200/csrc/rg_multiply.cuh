@@ -199,12 +199,13 @@ __device__ __forceinline__ int compute_p_max(int m_max) {   // RG.py:125-128
     return best;
 }
 
-// RG.compute_m_s (RG.py:130-150), n0 = 1, ell = 2.  Y records must hold the unscaled y.
+// RG.compute_m_s (RG.py:130-150); the fused path calls it with the reference's defaults n0 = 1, ell = 2 (RG.py:155).
+// Y records must hold the unscaled y.
 template <int J, bool BIG>
-__device__ __noinline__ void compute_m_s(Ctx& c, double a0, int& m_out, double& s_out, double& norm1_out) {
+__device__ __noinline__ void compute_m_s(Ctx& c, double a0, int& m_out, double& s_out, double& norm1_out,
+                                         const double n0 = 1.0, const double ell = 2.0) {
     const DevPlan& P = RG_PLAN(c);
     const int m_max = P.n_theta;
-    const double n0 = 1.0, ell = 2.0;
     bool have = false;
     double best_m = 0.0, best_s = 0.0;
     const double norm_ls = onenormest_pow<J, BIG>(c, a0, 1);
@@ -240,11 +241,16 @@ __device__ __noinline__ int expm_multiply(Ctx& c, double* f, double a_unscaled) 
     int m_star; double scale, n1;
     build_Y<J, BIG>(c, 1.0, 1.0, false);
     __syncthreads();
+    // the estimator applies L_y to probe vectors (+-1 columns, sign matrices, unit vectors) that are NOT symmetric
+    // under nu -> -nu: the mirror shortcuts of build_G are for the series terms only
+    const int symm_saved = c.symm;
+    c.symm = 0;
     compute_m_s<J, BIG>(c, a_unscaled, m_star, scale, n1);
+    c.symm = symm_saved;
     int err = 0;
     // a non-finite or absurd scale would never terminate in the reference either (range(scale)); cap it
     const long long reps = (scale < 1e9) ? (long long)scale : 1000000000LL;
-    for (long long r = 0; r < reps && c.n_liou <= RG_PLAN(c).max_liouville; ++r) {
+    for (long long r = 0; r < reps && c.n_liou - c.budget_base <= RG_PLAN(c).max_liouville; ++r) {
         const int e = expm_series<J, BIG>(c, f, a_unscaled, 1.0, scale, true, m_star);
         if (e) err = 1;
         __syncthreads();

@@ -1,3 +1,19 @@
+# Portions of this file (RG.__init__'s table construction, Hamiltonian, compute_p_max, generate_1Hamiltonian /
+# generate_2Hamiltonians) reproduce lines of cchandre/RG, RG.py, so that the class stays drop-in and the tables
+# uploaded to the GPU are the reference's own:
+#   BSD 2-Clause License -- Copyright (c) 2021, Cristel Chandre.  All rights reserved.
+#   Redistribution and use in source and binary forms, with or without modification, are permitted provided that the
+#   following conditions are met: 1. Redistributions of source code must retain the above copyright notice, this
+#   list of conditions and the following disclaimer.  2. Redistributions in binary form must reproduce the above
+#   copyright notice, this list of conditions and the following disclaimer in the documentation and/or other
+#   materials provided with the distribution.
+#   THIS SOFTWARE IS PROVIDED BY THE COPYRIGHT HOLDERS AND CONTRIBUTORS "AS IS" AND ANY EXPRESS OR IMPLIED WARRANTIES,
+#   INCLUDING, BUT NOT LIMITED TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND FITNESS FOR A PARTICULAR PURPOSE ARE
+#   DISCLAIMED.  IN NO EVENT SHALL THE COPYRIGHT HOLDER OR CONTRIBUTORS BE LIABLE FOR ANY DIRECT, INDIRECT, INCIDENTAL,
+#   SPECIAL, EXEMPLARY, OR CONSEQUENTIAL DAMAGES (INCLUDING, BUT NOT LIMITED TO, PROCUREMENT OF SUBSTITUTE GOODS OR
+#   SERVICES; LOSS OF USE, DATA, OR PROFITS; OR BUSINESS INTERRUPTION) HOWEVER CAUSED AND ON ANY THEORY OF LIABILITY,
+#   WHETHER IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING NEGLIGENCE OR OTHERWISE) ARISING IN ANY WAY OUT OF THE
+#   USE OF THIS SOFTWARE, EVEN IF ADVISED OF THE POSSIBILITY OF SUCH DAMAGE.
 """Host-side mirror of the reference's `RG` class and `Hamiltonian` (RG.py:44-332).
 
 Same constructor (the RG_dict parameter dictionary), same attributes, same method names, argument
@@ -277,6 +293,24 @@ class RG:
         _lib.check(_lib.lib().rg_norm(self._plan(), f.shape[0], f.ctypes.data, which, out.ctypes.data))
         return out
 
+    def sym_batch(self, f):
+        """RG.sym (RG.py:249-253) on a batch f[B, ...]; returns ndarray[B, ...]."""
+        f = _f64(f).reshape(-1, int(self.vecjl))
+        out = xp.empty_like(f)
+        _lib.check(_lib.lib().rg_sym(self._plan(), f.shape[0], f.ctypes.data, out.ctypes.data))
+        return out.reshape((-1,) + self.r_jl)
+
+    def reindex_rescale_batch(self, f, Omega, k0=None):
+        """Head of RG.rg_map (RG.py:210-216) on a batch f[B, ...] sharing the starting Omega: re-indexing by N and
+        rescaling with the frequency table row k0[b] (default 0 = the first rg_map from Omega)."""
+        nrm, onu, oms, tab = self._tables(Omega)
+        f = _f64(f).reshape(-1, int(self.vecjl))
+        out = xp.empty_like(f)
+        k0p = None if k0 is None else xp.ascontiguousarray(k0, dtype=xp.int32)
+        _lib.check(_lib.lib().rg_reindex_rescale(self._plan(), tab, f.shape[0], f.ctypes.data,
+                                                  None if k0p is None else k0p.ctypes.data, out.ctypes.data))
+        return out.reshape((-1,) + self.r_jl)
+
     # ------------------------------------------------------------------ RG.py:102-117
     def conv_product(self, fun1, fun2):
         a, b = _f64(fun1), _f64(fun2)
@@ -309,24 +343,26 @@ class RG:
         p_low, p_high = int(xp.floor(sqrt_m_max)), int(xp.ceil(sqrt_m_max + 1))
         return max(p for p in range(p_low, p_high + 1) if p * (p - 1) <= m_max + 1)
 
-    def _m_s(self, y):
+    def pnorm(self, y, p=1):
+        """RG.py:119-123: onenormest((L_y)**p)**(1/p) with the device restatement of scipy's block estimator."""
+        onu = self._Omega_nu_flat()
+        y0 = xp.array([y[0]], dtype=xp.float64)
+        y1, y2 = _f64(y[1]), _f64(y[2])
+        out = xp.zeros(1)
+        _lib.check(_lib.lib().rg_pnorm(self._plan(), 1, y0.ctypes.data, y1.ctypes.data, y2.ctypes.data, onu.ctypes.data,
+                                       int(p), out.ctypes.data))
+        return float(out[0])
+
+    def compute_m_s(self, y, n0=1, tol=2**-53, ell=2):
+        """RG.py:130-150; `tol` is accepted and unused, as in the reference."""
         onu = self._Omega_nu_flat()
         y0 = xp.array([y[0]], dtype=xp.float64)
         y1, y2 = _f64(y[1]), _f64(y[2])
         m, s = xp.zeros(1, xp.int32), xp.zeros(1, xp.int32)
         n1 = xp.zeros(1)
         _lib.check(_lib.lib().rg_compute_m_s(self._plan(), 1, y0.ctypes.data, y1.ctypes.data, y2.ctypes.data, onu.ctypes.data,
-                                             m.ctypes.data, s.ctypes.data, n1.ctypes.data))
-        return int(m[0]), int(s[0]), float(n1[0])
-
-    def pnorm(self, y, p=1):
-        if p != 1:
-            raise NotImplementedError("pnorm(p>1) is evaluated inside compute_m_s on the device")
-        return self._m_s(y)[2]
-
-    def compute_m_s(self, y, n0=1, tol=2**-53, ell=2):
-        m, s, _ = self._m_s(y)
-        return m, s
+                                             float(n0), float(ell), m.ctypes.data, s.ctypes.data, n1.ctypes.data))
+        return int(m[0]), int(s[0])
 
     # ------------------------------------------------------------------ RG.py:152-205
     def _expm(self, ct, h, y, step):
@@ -472,6 +508,11 @@ class RG:
                 h_list[i].count = int(count[q])
                 h_list[i].error = int(err[q])
                 res[i] = bool(conv[q])
+        # -99 / -98 are not results: the reference would still be iterating (RG.py:281, quirk Q6)
+        self.last_undecided = [i for i, h in enumerate(h_list) if h.error <= -98]
+        if self.last_undecided:
+            warnings.warn('converge: %d Hamiltonian(s) left undecided (error -99: iterate table exhausted, -98: work budget '
+                          'RG_B200_MAX_LIOUVILLE exhausted); they are reported as not converged' % len(self.last_undecided))
         return res
 
     # ------------------------------------------------------------------ RG.py:292-307
@@ -502,6 +543,9 @@ class RG:
                 tree.append(nxt)
             flat = [node[2] for level in tree for node in level]
             conv = self.converge_batch(flat)
+            if self.last_undecided:
+                raise _lib.RGError("approach: a midpoint of the bisection was left undecided (error %d); raise "
+                                   "RG_B200_MAX_LIOUVILLE" % flat[self.last_undecided[0]].error)
             pos, off = 0, 0
             for level in range(depth):
                 a, b, m = tree[level][pos]
@@ -542,12 +586,19 @@ class RG:
         _lib.check(_lib.lib().rg_approach(self._plan(), tab, n, f0.ctypes.data, f1.ctypes.data, float(reldist),
                                           c0.ctypes.data, c1.ctypes.data, e0.ctypes.data, e1.ctypes.data, lv.ctypes.data,
                                           self._stats()))
+        failed = []
         for q, p in enumerate(pairs):
-            if e0[q] < 0 or e1[q] <= -98:
-                raise _lib.RGError("approach: pair %d stopped with error %d (iterate table or work budget exhausted)" % (q, min(e0[q], e1[q])))
-            p[0].f, p[0].count, p[0].error = f0[q].reshape(self.r_jl).copy(), int(c0[q]), 0
-            p[1].f, p[1].count, p[1].error = f1[q].reshape(self.r_jl).copy(), int(c1[q]), 0     # RG.py:306
+            bad = int(min(e0[q], e1[q])) if (e0[q] <= -98 or e1[q] <= -98) else 0
+            p[0].f, p[0].count, p[0].error = f0[q].reshape(self.r_jl).copy(), int(c0[q]), bad
+            p[1].f, p[1].count, p[1].error = f1[q].reshape(self.r_jl).copy(), int(c1[q]), bad     # RG.py:306 (0 when decided)
+            if bad:
+                failed.append(q)
+        if failed:
+            # one undecided midpoint stops that pair only; the other pairs' results stand
+            warnings.warn('approach_batch: pair(s) %s stopped early with error -99/-98 (iterate table or work budget '
+                          'RG_B200_MAX_LIOUVILLE exhausted at a midpoint); their brackets are not refined to reldist' % failed)
         self.last_levels = lv
+        self.last_failed_pairs = failed
         return pairs
 
     # ------------------------------------------------------------------ batched region points (RG_modules.py:121-125)

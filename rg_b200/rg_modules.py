@@ -1,3 +1,18 @@
+# Portions of this file (the bodies of compute_iterates, compute_line, save_data and plot_fun) reproduce lines of
+# cchandre/RG, RG_modules.py, so that the drivers stay drop-in:
+#   BSD 2-Clause License -- Copyright (c) 2021, Cristel Chandre.  All rights reserved.
+#   Redistribution and use in source and binary forms, with or without modification, are permitted provided that the
+#   following conditions are met: 1. Redistributions of source code must retain the above copyright notice, this
+#   list of conditions and the following disclaimer.  2. Redistributions in binary form must reproduce the above
+#   copyright notice, this list of conditions and the following disclaimer in the documentation and/or other
+#   materials provided with the distribution.
+#   THIS SOFTWARE IS PROVIDED BY THE COPYRIGHT HOLDERS AND CONTRIBUTORS "AS IS" AND ANY EXPRESS OR IMPLIED WARRANTIES,
+#   INCLUDING, BUT NOT LIMITED TO, THE IMPLIED WARRANTIES OF MERCHANTABILITY AND FITNESS FOR A PARTICULAR PURPOSE ARE
+#   DISCLAIMED.  IN NO EVENT SHALL THE COPYRIGHT HOLDER OR CONTRIBUTORS BE LIABLE FOR ANY DIRECT, INDIRECT, INCIDENTAL,
+#   SPECIAL, EXEMPLARY, OR CONSEQUENTIAL DAMAGES (INCLUDING, BUT NOT LIMITED TO, PROCUREMENT OF SUBSTITUTE GOODS OR
+#   SERVICES; LOSS OF USE, DATA, OR PROFITS; OR BUSINESS INTERRUPTION) HOWEVER CAUSED AND ON ANY THEORY OF LIABILITY,
+#   WHETHER IN CONTRACT, STRICT LIABILITY, OR TORT (INCLUDING NEGLIGENCE OR OTHERWISE) ARISING IN ANY WAY OUT OF THE
+#   USE OF THIS SOFTWARE, EVEN IF ADVISED OF THE POSSIBILITY OF SUCH DAMAGE.
 """Drivers of the reference (RG_modules.py:48-201) on top of the batched device path.
 
 Same entry points and outputs: compute_iterates / compute_line / compute_surface / compute_region,
@@ -32,7 +47,7 @@ def shard_indices(n, rank, world):
     return xp.arange(rank, n, world)
 
 
-def gather_sharded(local, n, rank, world):
+def gather_sharded(local, n, rank, world, device=None):
     """All-gather equally padded int32 shards [n_local, C] and undo the cyclic interleave.
     The only collective of the path: results are 3 x int32 per point."""
     if world == 1:
@@ -46,7 +61,7 @@ def gather_sharded(local, n, rank, world):
     use_cuda = dist.get_backend() == "nccl"
     t = torch.from_numpy(pad)
     if use_cuda:
-        t = t.cuda()
+        t = t.cuda(device) if device is not None else t.cuda()
     parts = [torch.empty_like(t) for _ in range(world)]
     dist.all_gather(parts, t)
     g = torch.stack(parts).cpu().numpy()
@@ -120,13 +135,16 @@ def compute_cr_batch(epsilons, case):
     active = []
     for i, p in enumerate(pairs):
         c0, c1 = conv[2 * i], conv[2 * i + 1]
-        if c0 and not c1:
+        if c0 and not c1 and p[0].error > -98 and p[1].error > -98:
             active.append(i)
         else:
             out[i] = [2 * p[0].f[case.ModesK[0]], xp.nan]
     done = case.approach_batch([pairs[i] for i in active], case.RelDist)
     for i, p in zip(active, done):
-        out[i] = [2 * p[0].f[_] for _ in case.ModesK]
+        if p[0].error <= -98:      # this column's bisection hit the work budget: undecided, like a column without a bracket
+            out[i] = [2 * p[0].f[case.ModesK[0]], xp.nan]
+        else:
+            out[i] = [2 * p[0].f[_] for _ in case.ModesK]
     return out
 
 
@@ -147,9 +165,10 @@ def compute_surface(case):
     epsilon = xp.linspace(0, 1, case.Nxy, dtype=case.Precision)
     rank, world = _dist()
     idx = shard_indices(len(epsilon), rank, world)
-    local = xp.array(compute_cr_batch([epsilon[i] for i in idx], case), dtype=xp.float64).reshape(len(idx), -1)
+    local = xp.array(compute_cr_batch([epsilon[i] for i in idx], case), dtype=xp.float64).reshape(len(idx), max(2, len(case.ModesK)))
     if world > 1:
-        full = gather_sharded(local.view(xp.int64).reshape(len(idx), -1), len(epsilon), rank, world).view(xp.float64)
+        full = gather_sharded(local.view(xp.int64).reshape(len(idx), local.shape[1]), len(epsilon), rank, world,
+                              device=case._device_index()).view(xp.float64)
     else:
         full = local
     data = xp.array(full).T
@@ -197,18 +216,43 @@ def region_maps(case, x_vec, y_vec):
     # to three grid points wide whose neighbours belong to other ranks -- so it stays off by default.)
     conv, count, err = case.points(amps[idx])
     local = xp.stack([conv, count, err], axis=1).astype(xp.int32)
-    full = gather_sharded(local, n, rank, world)
+    full = gather_sharded(local, n, rank, world, device=case._device_index())
     data = xp.stack([full[:, 0], full[:, 1]], axis=1).astype(xp.int64).reshape(len(y_vec), len(x_vec), 2)
     info = full[:, 2].astype(xp.int64).reshape(len(y_vec), len(x_vec))
     return data, info
+
+
+def partial_save_rows(case):
+    """Rows of the region grid between two partial saves.  The reference re-saves the partial `data`/`info` after every
+    y-row (RG_modules.py:138-143); `PartialSaveRows` in the parameter dict (not an RG_dict key: optional) selects the
+    cadence here -- 1 = exactly the reference's, 0 = only the final save; default: Nxy/16 rows per launch when
+    SaveData is on (every launch ends with a tail of idle SMs, so the reference's cadence costs GPU throughput), one
+    launch for the whole grid when it is off."""
+    rows = getattr(case, 'PartialSaveRows', None)
+    if rows is None:
+        rows = max(1, case.Nxy // 16) if case.SaveData else 0
+    return int(rows)
 
 
 def compute_region(case):
     print('\033[92m    {} -- region \033[00m'.format(case.__str__()))
     timestr = time.strftime("%Y%m%d_%H%M")
     x_vec, y_vec = (xp.linspace(case.AmpInf[_], case.AmpSup[_], case.Nxy, dtype=case.Precision) for _ in range(2))
-    data, info = region_maps(case, x_vec, y_vec)
     rank, _ = _dist()
+    rows = partial_save_rows(case)
+    if rows <= 0 or rows >= len(y_vec):
+        data, info = region_maps(case, x_vec, y_vec)
+    else:
+        # RG_modules.py:138-143: the partial maps (rows done so far) overwrite the same file after every block of rows
+        blocks_d, blocks_i = [], []
+        for r0 in range(0, len(y_vec), rows):
+            d, i = region_maps(case, x_vec, y_vec[r0:r0 + rows])
+            blocks_d.append(d)
+            blocks_i.append(i)
+            if rank == 0 and r0 + rows < len(y_vec):
+                save_data('region', xp.concatenate(blocks_d).reshape((-1, case.Nxy, 2)), timestr, case,
+                          xp.concatenate(blocks_i).reshape((-1, case.Nxy)))
+        data, info = xp.concatenate(blocks_d), xp.concatenate(blocks_i)
     if rank == 0:
         save_data('region', data, timestr, case, info=info, display=True)
     if case.PlotResults and rank == 0:

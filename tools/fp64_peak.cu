@@ -12,7 +12,7 @@
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { fprintf(stderr, "CUDA %s at %s:%d\n", cudaGetErrorString(e), __FILE__, __LINE__); exit(1); } } while (0)
 
 template <int NCHAIN>
-__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double a, double b) {
+__global__ void __launch_bounds__(512) dfma_kernel(double* out, int iters, double a, double b) {
     double acc[NCHAIN];
 #pragma unroll
     for (int i = 0; i < NCHAIN; ++i) acc[i] = threadIdx.x * 1e-9 + i;
@@ -93,12 +93,14 @@ template <typename F>
 float time_ms(F launch, int reps) {
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    launch(); launch();
+    launch(); CK(cudaGetLastError());   // a refused launch (e.g. more threads than __launch_bounds__) must not be timed
+    launch();
     CK(cudaDeviceSynchronize());
     float best = 1e30f;
     for (int r = 0; r < reps; ++r) {
         CK(cudaEventRecord(e0));
         launch();
+        CK(cudaGetLastError());
         CK(cudaEventRecord(e1));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
