@@ -46,7 +46,10 @@ def parse():
     ap.add_argument("--no-other-ct", action="store_true", help="skip the expm_multiply / expm_adapt side measurements")
     ap.add_argument("--port", action="store_true", help="reference arm: time the C port (oracle/rg_oracle.c) instead of the reference files")
     ap.add_argument("--dump-map", type=int, default=0, help="reference arm: add the sample's (conv, count, error) map to the JSON line")
-    ap.add_argument("--neighbour-queue", action="store_true", help="experimental: heavy points queue their grid neighbours")
+    ap.add_argument("--config", type=int, default=4, choices=[3, 4, 5],
+                    help="BASELINE.json config: 4 = region Nxy=256 L=J=10 (the headline, default); 3 = surface Nxy=128 L=J=10 "
+                         "sharded over the ranks; 5 = spiral-mean n=3 region L=J=6 expm_multiply (sub-grid, see --sub)")
+    ap.add_argument("--sub", type=int, default=32, help="config 5: side of the strided sub-grid of the Nxy=128 region (128 = all)")
     ap.add_argument("--emulate-world", type=int, default=0,
                     help="diagnostic: run rank 0's shard of an N-rank job on one GPU (tail / load-balance study)")
     return ap.parse_args()
@@ -287,7 +290,6 @@ def main_b200(a):
         n_total = len(idx)
     n_loc = len(idx)
     eff_world = a.emulate_world if a.emulate_world > 1 else world
-    row_len = a.nxy // eff_world if (a.nxy % eff_world == 0 and a.neighbour_queue) else 0
     # host pinned buffers (the public-API path copies them in and out inside the timed region)
     h_amps = torch.from_numpy(amps[idx].copy()).pin_memory()
     h_out = [torch.zeros(n_loc, dtype=torch.int32).pin_memory() for _ in range(3)]
@@ -304,7 +306,7 @@ def main_b200(a):
         flush.fill_(1)                       # L2 flush between iterations
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        case.points(h_amps, *h_out, row_len=row_len)   # H2D + kernel + D2H through the C ABI
+        case.points(h_amps, *h_out)   # H2D + kernel + D2H through the C ABI
         loc = np.stack([t.numpy() for t in h_out], axis=1)
         full = rg_modules.gather_sharded(loc, n_total, rank, world)
         wall = time.perf_counter() - t0
@@ -408,9 +410,172 @@ def main_b200(a):
     case.close()
 
 
+# ---------------------------------------------------------------------------------------------- configs 3 and 5
+def _dist_setup():
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return torch, dist, world, rank, local, json_fd
+
+
+def main_config3(a):
+    """BASELINE config 3: compute_surface, Nxy=128 columns of the critical surface, L=J=10, RelDist=1e-7, columns sharded
+    cyclically over the ranks, one all_gather of the float64[2][Nxy] result (RG_modules.py:92-119).  One step = the
+    whole surface.  value = columns/s (wall clock between barriers, max over ranks: the two launches per rank --
+    batched converge of the brackets, batched on-device bisection -- are synchronous ABI calls)."""
+    torch, dist, world, rank, local, json_fd = _dist_setup()
+    from rg_b200 import RG, make_param_dict
+    from rg_b200 import rg_modules
+    import io, contextlib
+    nxy = 128
+    case = RG(make_param_dict(L=GRID["L"], J=GRID["J"], Nxy=nxy, AmpInf=GRID["AmpInf"], AmpSup=GRID["AmpSup"], RelDist=1e-7,
+                              CanonicalTransformation=a.ct, SaveData=False, Method="surface"), device=local)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step():
+        with contextlib.redirect_stdout(io.StringIO()):
+            return rg_modules.compute_surface(case)
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    data = None
+    for _ in range(a.steps):
+        data = step()
+    barrier()
+    dt = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    if rank == 0:
+        import hashlib
+        line = {"metric": "critical-surface columns/sec (Nxy=128, L=J=10, RelDist=1e-7)", "value": a.steps * nxy / dt, "unit": "columns/s",
+                "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE config 3: compute_surface Nxy=128, L=J=10, golden mean, %s, RelDist=1e-7; %d columns per rank "
+                                       "(cyclic), 2 launches per rank (bracket converge, on-device bisection)" % (a.ct, (nxy + world - 1) // world)},
+                "gpu_launches": 2 * a.steps * world, "clocks": sampler.summary(),
+                "result": {"columns_with_threshold": int(np.isfinite(data[1]).sum()), "eps2_min": float(np.nanmin(data[1])),
+                           "eps2_max": float(np.nanmax(data[1])), "sha1_of_data": hashlib.sha1(np.ascontiguousarray(data).tobytes()).hexdigest()}}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    case.close()
+
+
+def main_config5(a):
+    """BASELINE config 5: spiral-mean torus n=3, region Nxy=128, L=J=6, expm_multiply -- the global-record (BIG) kernel.
+    One step = the --sub x --sub strided sub-grid of the region (default 32x32 = 1024 points; 128 = the whole grid),
+    sharded cyclically over the ranks."""
+    torch, dist, world, rank, local, json_fd = _dist_setup()
+    from rg_b200 import RG, make_param_dict
+    from rg_b200 import rg_modules
+    from rg_b200.rg_dict import SPIRAL_MEAN
+    nxy, side = 128, a.sub
+    stride = nxy // side
+    case = RG(make_param_dict(L=6, J=6, Nxy=nxy, CanonicalTransformation=a.ct, SaveData=False, **SPIRAL_MEAN), device=local)
+    xs = np.linspace(case.AmpInf[0], case.AmpSup[0], nxy)[stride // 2::stride]
+    ys = np.linspace(case.AmpInf[1], case.AmpSup[1], nxy)[stride // 2::stride]
+    amps = rg_modules.region_amps(case, xs, ys)
+    idx = rg_modules.shard_indices(len(amps), rank, world)
+    h_amps = torch.from_numpy(amps[idx].copy()).pin_memory()
+    h_out = [torch.zeros(len(idx), dtype=torch.int32).pin_memory() for _ in range(3)]
+    info = case.plan_info()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def step():
+        t0 = time.perf_counter()
+        case.points(h_amps, *h_out)
+        loc = np.stack([t.numpy() for t in h_out], axis=1)
+        full = rg_modules.gather_sharded(loc, len(amps), rank, world)
+        return time.perf_counter() - t0, case.last_stats, full
+    for _ in range(a.warmup):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t_begin = time.perf_counter()
+    wall = dev = 0.0
+    liou = useful = executed = 0
+    for _ in range(a.steps):
+        w, st, full = step()
+        wall += w
+        dev += st.kernel_ms * 1e-3
+        liou += st.liouville
+        useful += st.conv_fma_useful
+        executed += st.conv_fma_executed
+    barrier()
+    bracket = time.perf_counter() - t_begin
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    if world > 1:
+        t = torch.tensor([dev, wall, bracket], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_max, wall_max, bracket = (float(v) for v in t.tolist())
+    else:
+        dev_max, wall_max = dev, wall
+    if rank == 0:
+        peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")))["dfma_tflops"]
+        ach = 2.0 * useful / dev * 1e-12
+        line = {"metric": "region grid points/sec (spiral mean n=3, Nxy=128, L=J=6, %s)" % a.ct, "value": a.steps * len(amps) / dev_max,
+                "unit": "points/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": bracket / a.steps * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE config 5: spiral-mean torus N=[[0,1,0],[0,0,1],[1,0,-1]], region Nxy=128, L=J=6, %s; "
+                                       "%dx%d strided sub-grid (ix,iy = %d, %d, ...) = %d points over %d rank(s)"
+                                       % (a.ct, side, side, stride // 2, stride // 2 + stride, len(amps), world),
+                           "threads_per_cta": info["threads_per_cta"], "smem_bytes_per_cta": info["smem_bytes"],
+                           "ctas_per_sm": info["ctas_per_sm"], "records": "global (BIG kernel): 246 KB of g records per Hamiltonian"},
+                "e2e": {"value": a.steps * len(amps) / wall_max, "unit": "points/s", "h2d_bytes_per_step": int(h_amps.numel() * 8),
+                        "d2h_bytes_per_step": int(3 * len(idx) * 4)},
+                "gpu_launches": a.steps * world,
+                "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                             "kernel": "rg_kernel<6, true> (global-record variant)", "liouville_evaluations": int(liou),
+                             "useful_flop_per_liouville": 2 * info["fma_useful_per_liouville"],
+                             "issued_flop_per_liouville": 2 * info["fma_executed_per_liouville"],
+                             "issued_tflops": 2.0 * executed / dev * 1e-12,
+                             "dense_equivalent_tflops": liou * 229.4e6 / dev * 1e-12,
+                             "peak_source": "measured DFMA peak, tools/fp64_peak.cu (profiles/fp64_peak_r01.json)"},
+                "clocks": sampler.summary(),
+                "result_checksum": {"converged": int(full[:, 0].sum()), "count_sum": int(full[:, 1].sum()),
+                                    "errors": {str(k): int(v) for k, v in zip(*np.unique(full[:, 2], return_counts=True))}}}
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    case.close()
+
+
 if __name__ == "__main__":
     args = parse()
     if args.impl == "reference":
         main_reference(args)
+    elif args.config == 3:
+        main_config3(args)
+    elif args.config == 5:
+        if "--ct" not in sys.argv and "RG_BENCH_CT" not in os.environ:
+            args.ct = "expm_multiply"          # BASELINE config 5 names it
+        main_config5(args)
     else:
         main_b200(args)

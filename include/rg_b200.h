@@ -109,14 +109,10 @@ int rg_tables_destroy(rg_tables* t);
 int rg_region(rg_plan* plan, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
               int32_t* conv, int32_t* count, int32_t* err, rg_stats* stats);
 
-/* rg_region with scheduling controls.  liouville_per_point (int64 [n], may be NULL) receives the liouville
-   evaluations each point needed.  row_len > 0 declares the points to be a row-major grid with rows of
-   row_len points: a point that has already spent hot_threshold evaluations (0 = default 1500) queues its
-   four grid neighbours ahead of the ticket, because the heavy points hug the critical surface and must
-   start early for the tail of the launch to stay short.  Results never depend on the processing order. */
+/* rg_region that also reports the work: liouville_per_point (int64 [n], may be NULL) receives the liouville
+   evaluations each point needed (the roofline numerator, and the input of load-balance studies). */
 int rg_region_work(rg_plan* plan, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
-                   int32_t* conv, int32_t* count, int32_t* err, int64_t* liouville_per_point,
-                   int32_t row_len, int32_t hot_threshold, rg_stats* stats);
+                   int32_t* conv, int32_t* count, int32_t* err, int64_t* liouville_per_point, rg_stats* stats);
 
 /* RG.converge batched (RG.py:278-290).  f [n][vecjl]; k0[n] = iterate index of each input's Omega in
    `tab` (may be NULL = all 0); err_io[n] carries h.error in and out (untouched on the converged branch). */

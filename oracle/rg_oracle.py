@@ -412,6 +412,14 @@ def default_params(**over):
                  K=((0, 1, 0, 0), (0, 0, 1, 0), (0, 0, 0, 1)),
                  AmpInf=[0, 0, 0], AmpSup=[0.05, 0.25, 0.1], CoordLine=[0, 0.05],
                  ModesLine=xp.asarray((1, 1, 0)), DirLine=xp.asarray([1, 5, 0.1]))
+    elif torus == "taumean":   # RG_dict.py:36-46
+        tau = 0.445041867912629
+        p.update(N=xp.asarray([[0, 1, -1], [1, -1, 1], [0, -1, 2]], dtype=int),
+                 omega0=xp.asarray([1.0, tau, 1.0 - tau - tau ** 2], dtype=Precision),
+                 Omega=xp.asarray([1, 1, -1], dtype=Precision),
+                 K=((0, 0, -1, 1), (0, 1, -1, -1), (0, 0, 0, 1)),
+                 AmpInf=[0.0, 0.0, 0.01], AmpSup=[7e-4, 6e-3, 0.01], CoordLine=[0.0, 0.002],
+                 ModesLine=xp.asarray((1, 1, 0)), DirLine=xp.asarray([1, 5, 0.01]))
     ct = over.pop("CT", None)
     if ct is not None:
         p['CanonicalTransformation'] = 'self.' + ct

@@ -49,8 +49,7 @@ SIGNATURES = {
     "rg_tables_create": (ctypes.c_int, [vp, ctypes.c_int32, vp, vp, ctypes.POINTER(vp)]),
     "rg_tables_destroy": (ctypes.c_int, [vp]),
     "rg_region": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, ctypes.POINTER(RGStats)]),
-    "rg_region_work": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, vp, ctypes.c_int32,
-                                      ctypes.c_int32, ctypes.POINTER(RGStats)]),
+    "rg_region_work": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_converge": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, vp, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_approach": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_double, vp, vp, vp, vp, vp, ctypes.POINTER(RGStats)]),
     "rg_map": (ctypes.c_int, [vp, vp, ctypes.c_int32, vp, vp, ctypes.c_int32, vp, vp, ctypes.POINTER(RGStats)]),
@@ -75,11 +74,14 @@ SIGNATURES = {
 def build(force=False, verbose=False):
     """Compile librg_b200.so in-tree for sm_100a."""
     csrc = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(csrc, f) for f in ("rg_b200.cu", "rg_device.cuh", "rg_multiply.cuh", "rg_plan.hpp")]
+    srcs = [os.path.join(csrc, f) for f in ("rg_b200.cu", "rg_kernel_inst.cu", "rg_kernel.cuh", "rg_device.cuh", "rg_multiply.cuh",
+                                            "rg_plan.hpp", "Makefile")]
     srcs.append(os.path.join(_HERE, "..", "include", "rg_b200.h"))
     if not force and os.path.exists(SO_PATH) and all(os.path.getmtime(SO_PATH) >= os.path.getmtime(s) for s in srcs):
         return SO_PATH
-    r = subprocess.run(["make", "-C", csrc, "-B"], capture_output=True, text=True)
+    if force:
+        subprocess.run(["make", "-C", csrc, "clean"], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", csrc], capture_output=True, text=True)   # one translation unit per Taylor order, in parallel
     if verbose or r.returncode != 0:
         print(r.stdout[-4000:], r.stderr[-4000:])
     if r.returncode != 0:

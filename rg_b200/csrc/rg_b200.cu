@@ -11,23 +11,37 @@
 
 #include "../../include/rg_b200.h"
 #include "rg_plan.hpp"
-#include "rg_device.cuh"
-#include "rg_multiply.cuh"
+#include "rg_kernel.cuh"   // Job, DevPlan, Tables and the small device helpers; the fused kernel itself is instantiated elsewhere
 
 using namespace rgdev;
 
-// Taylor orders J with a compiled kernel (the Taylor loops are fully unrolled per J).
-#ifdef RG_ONLY_J10   // quick experiment builds: nvcc -DRG_ONLY_J10 ... (only the L=J=10 shared-memory kernel)
-#define RG_J_LIST(X) X(10)
-#define RG_JBIG_LIST(X)
-#endif
-#ifndef RG_J_LIST
-#define RG_J_LIST(X) X(4) X(5) X(6) X(10)
-#endif
-// J values that also get the BIG kernel (operand records in global memory; arrays beyond one SM's shared memory)
-#ifndef RG_JBIG_LIST
-#define RG_JBIG_LIST(X) X(4) X(6)
-#endif
+// The fused kernel rg_kernel<J, BIG> is instantiated once per Taylor order J (its Taylor loops are fully unrolled) and
+// record placement (BIG = operand records in global memory, for arrays beyond one SM's shared memory), each in its own
+// translation unit (rg_kernel_inst.cu, compiled in parallel by the Makefile for J = 2..12).  The host side finds them
+// through weak symbols: an order the Makefile did not build (`make JS="10"` for quick experiments) is simply absent.
+#define RG_J_ALL(X) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12)
+#define RG_DECL(j)                                                                                         \
+    extern "C" const void* rg_inst_kernel_##j##_0(void) __attribute__((weak));                             \
+    extern "C" const void* rg_inst_kernel_##j##_1(void) __attribute__((weak));                             \
+    extern "C" int rg_inst_upload_##j##_0(const rgdev::DevPlan*, int) __attribute__((weak));               \
+    extern "C" int rg_inst_upload_##j##_1(const rgdev::DevPlan*, int) __attribute__((weak));
+RG_J_ALL(RG_DECL)
+#undef RG_DECL
+struct KernelInst { const void* kernel; int (*upload)(const rgdev::DevPlan*, int); };
+static KernelInst pick_inst(int J, bool big) {
+    KernelInst k{nullptr, nullptr};
+    switch (J) {
+#define RG_CASE(j)                                                                                         \
+    case j:                                                                                                \
+        if (big) { if (rg_inst_kernel_##j##_1) { k.kernel = rg_inst_kernel_##j##_1(); k.upload = rg_inst_upload_##j##_1; } } \
+        else { if (rg_inst_kernel_##j##_0) { k.kernel = rg_inst_kernel_##j##_0(); k.upload = rg_inst_upload_##j##_0; } }     \
+        break;
+        RG_J_ALL(RG_CASE)
+#undef RG_CASE
+        default: break;
+    }
+    return k;
+}
 
 // ------------------------------------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -41,291 +55,10 @@ static int fail(int code, const std::string& msg) { g_err = msg; return code; }
     } while (0)
 
 extern "C" const char* rg_last_error(void) { return g_err.c_str(); }
-#ifdef RG_DBG_BUSY   // experiment builds only (tools/probe_region.py PROBE_BUSY=1); not part of include/rg_b200.h
-extern "C" int rg_debug_busy(unsigned long long* out32) {
-    CU(cudaMemcpyFromSymbol(out32, rgdev::g_dbg_busy, 32 * sizeof(unsigned long long)));
-    return 0;
-}
-#endif
 extern "C" int rg_device_count(int* n) {
     cudaError_t e = cudaGetDeviceCount(n);
     if (e != cudaSuccess) { *n = 0; return fail((int)e, cudaGetErrorString(e)); }
     return 0;
-}
-
-// ------------------------------------------------------------------------------------------------ kernels
-struct Job {
-    int mode;  // 0 region (amps), 1 converge (f given), 2 rg_map x n_iter, 3 expm, 4 liouville, 5 generate_y, 6 compute_m_s,
-               // 7 approach (bisection of the pair f_in / f1_io)
-    int n;
-    int sched;  // 0 sparse, 1 dense (2 = sparse half-space is selected on the device)
-    int csize;  // thread-block cluster size: 1, 2 or 4 CTAs per Hamiltonian (modes 0-2 only)
-    int* ticket;
-    // inputs
-    const double* amps; const int* K_flat; int nK;   // mode 0 (K_flat: j*M + centred mode)
-    const double* f_in;                               // [n][vecjl] wrapped layout
-    const int* k0;                                    // may be null
-    int n_iter;
-    const double* y0; const double* y1; const double* y2; const double* y3;  // mode 3/4 (wrapped layout)
-    const double* Omega_nu;                           // [M] centred (mode 3/4/5)
-    double step; int ct;
-    // outputs
-    int* conv; int* count; int* err;
-    double* f_out; double* y0_out; double* y1_out; double* y2_out; double* y3_out;
-    long long* n_liou; long long* n_lie; long long* n_maps;
-    int* m_out; int* s_out; double* norm1_out;   // mode 6
-    int pnorm_p; double ms_n0, ms_ell;            // mode 6: pnorm_p > 0 -> RG.pnorm(y, p) only; else compute_m_s(y, n0, ell)
-    long long* liou_out;                          // optional per-item liouville count
-    // heavy-neighbour scheduling (region grids): a point that turns out heavy queues its grid neighbours
-    int* claimed; int* prio_q; int* q_ctr; int row_len; int hot_threshold; int q_cap;
-    double* ws_base;
-    // mode 7: the pair is (f_in -> f_out, f1_io); count/err hold the first end, count1/err1 the second
-    double* f1_io; int* count1; int* err1; int* levels; double reldist; int max_levels;
-};
-
-__device__ __forceinline__ void load_wrapped(const DevPlan& P, const double* __restrict__ src, double* __restrict__ dst) {
-    for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
-        const int j = i / P.M, c = i - j * P.M;
-        dst[i] = src[j * P.M + P.c2w[c]];
-    }
-}
-__device__ __forceinline__ void store_wrapped(const DevPlan& P, const double* __restrict__ src, double* __restrict__ dst) {
-    for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) {
-        const int j = i / P.M, c = i - j * P.M;
-        dst[j * P.M + P.c2w[c]] = src[i];
-    }
-}
-
-// ---- work distribution.  Default: an atomic ticket over the items in array order.  Region grids add a
-// priority queue: cost is spatially coherent (the heavy points hug the critical surface), so a point that
-// has already spent `hot_threshold` liouville evaluations queues its four grid neighbours; idle CTAs drain
-// that queue before the ticket.  Results do not depend on the order in which points are processed.
-__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
-
-__device__ int fetch_item(const Job& job) {
-    if (job.row_len > 0) {
-        for (;;) {
-            const int h = ld_volatile(&job.q_ctr[2]), t = ld_volatile(&job.q_ctr[1]);
-            if (h >= t) break;
-            if (atomicCAS(&job.q_ctr[2], h, h + 1) != h) continue;
-            const int it = ld_volatile(&job.prio_q[h]);
-            if (atomicCAS(&job.claimed[it], 0, 1) == 0) return it;
-        }
-        for (;;) {
-            const int i = atomicAdd(job.ticket, 1);
-            if (i >= job.n) return job.n;
-            if (atomicCAS(&job.claimed[i], 0, 1) == 0) return i;
-        }
-    }
-    return atomicAdd(job.ticket, 1);
-}
-
-__device__ void push_neighbours(const Job& job, int item) {
-    const int rl = job.row_len, col = item % rl;
-    const int nb[4] = {col > 0 ? item - 1 : -1, col + 1 < rl ? item + 1 : -1, item - rl, item + rl};
-    for (int q = 0; q < 4; ++q) {
-        const int it = nb[q];
-        if (it < 0 || it >= job.n || ld_volatile(&job.claimed[it]) != 0) continue;
-        const int slot = atomicAdd(&job.q_ctr[0], 1);
-        if (slot >= job.q_cap) continue;
-        job.prio_q[slot] = it;
-        __threadfence();
-        while (atomicCAS(&job.q_ctr[1], slot, slot + 1) != slot) {}   // publish in reservation order
-    }
-}
-
-template <int J, bool BIG>
-__global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ? 1 : 2) rg_kernel(const int slot, const __grid_constant__ Tables T, const __grid_constant__ Job job) {
-    namespace cg = cooperative_groups;
-    Ctx c;
-    c.slot = slot;
-    c.sidx = job.sched;
-    c.csize = job.csize;
-    c.cbase = job.csize == 4 ? 6 : (job.csize == 2 ? 3 : 0);
-    c.crank = job.csize > 1 ? (int)cg::this_cluster().block_rank() : 0;
-    const DevPlan& P = RG_PLAN(c);
-    int* sh_item = reinterpret_cast<int*>(smem_red() + 64);
-    c.ws = job.ws_base + (size_t)blockIdx.x * (size_t)P.ws_stride;
-    c.rec = reinterpret_cast<double2*>(c.ws + (size_t)P.rec_offset);
-    const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
-    c.Omega_nu = T.Omega_nu;
-    // zero all records once (pads and the all-zero record stay zero for the life of the CTA)
-    {
-        const int nd2 = (P.M + RG_ZERO_RECS + (BIG ? P.M : RG_SCHED(c).n_support)) * P.rec_units;
-        for (int i = threadIdx.x; i < nd2; i += blockDim.x) sm.G[i] = make_double2(0.0, 0.0);
-    }
-    double* fa = c.ws + (size_t)WS_FA * P.vecjl;
-    const int M = P.M, c0 = (M - 1) / 2;
-    for (;;) {
-        if (c.csize > 1) {
-            // one ticket per cluster: rank 0 draws it and posts it into every peer's shared memory
-            cg::cluster_group cl = cg::this_cluster();
-            cl.sync();
-            if (c.crank == 0 && threadIdx.x == 0) {
-                const int it = fetch_item(job);
-                for (int r = 0; r < c.csize; ++r) *cl.map_shared_rank(sh_item, r) = it;
-            }
-            cl.sync();
-        } else {
-            __syncthreads();
-            if (threadIdx.x == 0) *sh_item = fetch_item(job);
-            __syncthreads();
-        }
-        const int item = *sh_item;
-        if (item >= job.n) break;
-        c.n_liou = 0; c.n_lie = 0; c.budget_base = 0; c.symm = 0; c.t_conv = 0; c.t_epi = 0; c.t_busy = 0;
-        const long long t_item = clock64();
-        c.rng = 0x243F6A8885A308D3ull ^ ((uint64_t)(item + 1) * 0x9E3779B97F4A7C15ull);
-        long long n_maps = 0;
-        double* f = fa;
-        const int k0 = job.k0 ? job.k0[item] : 0;
-        if (job.mode == 0) {
-            // generate_1Hamiltonian(amps, symmetric=True)  RG.py:255-264
-            for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) f[i] = 0.0;
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                for (int q = 0; q < job.nK; ++q) f[job.K_flat[q]] = job.amps[(size_t)item * job.nK + q];
-                f[2 * M + c0] = 0.5;
-            }
-            __syncthreads();
-            sym_and_norms<J>(c, f, true);
-        } else if (job.mode != 6) {
-            load_wrapped(P, job.f_in + (size_t)item * P.vecjl, f);
-            __syncthreads();
-        }
-        if (job.mode == 0 || job.mode == 1) {
-            // RG.converge  RG.py:278-290
-            double2 nn = sym_and_norms<J>(c, f, false);
-            double ni = nn.y;
-            int k = 0, err = 0;
-            bool overflow = false, budget = false, hot = false;
-            while (P.tol_max > ni && ni > P.tol_min) {
-                if (k0 + k >= T.n_tab) { overflow = true; break; }
-                if (c.n_liou - c.budget_base > P.max_liouville) { budget = true; break; }
-                f = rg_map_dev<J, BIG>(c, f, T, k0 + k, err, ni);
-                ++k; ++n_maps;
-                if (job.row_len > 0 && !hot && c.n_liou > job.hot_threshold) {
-                    hot = true;
-                    if (threadIdx.x == 0 && c.crank == 0) push_neighbours(job, item);
-                }
-            }
-            if (threadIdx.x == 0 && c.crank == 0) {
-                const bool cv = (ni < P.tol_min) && !overflow && !budget;
-                job.conv[item] = cv ? 1 : 0;
-                job.count[item] = cv ? -k : k;
-                if (budget) job.err[item] = RG_ERR_WORK_BUDGET;
-                else if (overflow) job.err[item] = RG_ERR_TABLE_EXHAUSTED;
-                else if (!cv) job.err[item] = err;
-                else if (job.mode == 0) job.err[item] = 0;
-            }
-        } else if (job.mode == 2) {
-            int err = 0; double ni;
-            for (int k = 0; k < job.n_iter; ++k) {
-                if (k0 + k >= T.n_tab) { err = RG_ERR_TABLE_EXHAUSTED; break; }
-                f = rg_map_dev<J, BIG>(c, f, T, k0 + k, err, ni);
-                ++n_maps;
-            }
-            __syncthreads();
-            if (c.crank == 0) {
-                store_wrapped(P, f, job.f_out + (size_t)item * P.vecjl);
-                if (threadIdx.x == 0) job.err[item] = err;
-            }
-        } else if (job.mode == 3 || job.mode == 4) {
-            // caller-supplied y (wrapped) -> WS_Y1..3
-            c.Omega_nu = job.Omega_nu;
-            load_wrapped(P, job.y1 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y1 * P.vecjl);
-            load_wrapped(P, job.y2 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y2 * P.vecjl);
-            if (job.mode == 3) load_wrapped(P, job.y3 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y3 * P.vecjl);
-            __syncthreads();
-            const double a = job.y0[item];
-            if (job.mode == 3) {
-                int err = job.err[item];
-                if (job.ct == 0) err = expm_onestep<J, BIG>(c, f, a, job.step);
-                else if (job.ct == 1) err = expm_adapt<J, BIG>(c, f, a, job.step, err);
-                else err = expm_multiply<J, BIG>(c, f, a);
-                __syncthreads();
-                store_wrapped(P, f, job.f_out + (size_t)item * P.vecjl);
-                if (threadIdx.x == 0) job.err[item] = err;
-            } else {
-                // RG.liouville  RG.py:115-117
-                double* dst = c.ws + (size_t)WS_T0 * P.vecjl;
-                build_Y<J, BIG>(c, 1.0, 1.0, false);
-                liouville_apply<J, BIG>(c, f, dst, a, false);
-                __syncthreads();
-                store_wrapped(P, dst, job.f_out + (size_t)item * P.vecjl);
-            }
-        } else if (job.mode == 6) {
-            // RG.compute_m_s  RG.py:130-150
-            c.Omega_nu = job.Omega_nu;
-            load_wrapped(P, job.y1 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y1 * P.vecjl);
-            load_wrapped(P, job.y2 + (size_t)item * P.vecjl, c.ws + (size_t)WS_Y2 * P.vecjl);
-            __syncthreads();
-            build_Y<J, BIG>(c, 1.0, 1.0, false);
-            __syncthreads();
-            int m_star = 0; double scale = 0.0, n1;
-            if (job.pnorm_p > 0) {   // RG.pnorm(y, p)  RG.py:119-123
-                const double e = onenormest_pow<J, BIG>(c, job.y0[item], job.pnorm_p);
-                n1 = job.pnorm_p == 1 ? e : pow(e, 1.0 / (double)job.pnorm_p);
-            } else {
-                compute_m_s<J, BIG>(c, job.y0[item], m_star, scale, n1, job.ms_n0, job.ms_ell);
-            }
-            if (threadIdx.x == 0) {
-                job.m_out[item] = m_star;
-                job.s_out[item] = scale < 2147483647.0 ? (int)scale : 2147483647;
-                job.norm1_out[item] = n1;
-            }
-        } else if (job.mode == 7) {
-            // RG.approach (RG.py:292-307): the whole bisection of one pair, no host round trip per level
-            double* a0 = c.ws + (size_t)WS_A0 * P.vecjl;
-            double* a1 = c.ws + (size_t)WS_A1 * P.vecjl;
-            double* am = c.ws + (size_t)WS_AM * P.vecjl;
-            load_wrapped(P, job.f_in + (size_t)item * P.vecjl, a0);
-            load_wrapped(P, job.f1_io + (size_t)item * P.vecjl, a1);
-            __syncthreads();
-            int cnt0 = job.count[item], cnt1 = job.count1[item], e1 = job.err1[item];
-            int levels = 0, bad = 0;
-            for (;;) {
-                const double2 dn = diff_norms<J>(c, a0, a1, true);
-                if (!(dn.x > job.reldist * dn.y) || levels >= job.max_levels) break;
-                f = fa;
-                for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) { const double m = (a0[i] + a1[i]) * 0.5; am[i] = m; f[i] = m; }
-                __syncthreads();
-                bool cv; int err, status;
-                const int k = converge_dev<J, BIG>(c, f, T, k0, cv, err, status, n_maps);
-                ++levels;
-                if (status) { bad = status == 1 ? RG_ERR_TABLE_EXHAUSTED : RG_ERR_WORK_BUDGET; break; }
-                __syncthreads();
-                copy_arr(c, cv ? a0 : a1, am);
-                if (cv) cnt0 = -k; else { cnt1 = k; e1 = err; }
-                __syncthreads();
-            }
-            if (c.crank == 0) {
-                store_wrapped(P, a0, job.f_out + (size_t)item * P.vecjl);
-                store_wrapped(P, a1, job.f1_io + (size_t)item * P.vecjl);
-                if (threadIdx.x == 0) {
-                    job.count[item] = cnt0; job.count1[item] = cnt1;
-                    job.err1[item] = bad ? bad : e1;
-                    if (bad) job.err[item] = bad;
-                    job.levels[item] = levels;
-                }
-            }
-        } else if (job.mode == 5) {
-            c.Omega_nu = job.Omega_nu;
-            const double a = generate_y<J>(c, f);
-            __syncthreads();
-            store_wrapped(P, c.ws + (size_t)WS_Y1 * P.vecjl, job.y1_out + (size_t)item * P.vecjl);
-            store_wrapped(P, c.ws + (size_t)WS_Y2 * P.vecjl, job.y2_out + (size_t)item * P.vecjl);
-            store_wrapped(P, c.ws + (size_t)WS_Y3 * P.vecjl, job.y3_out + (size_t)item * P.vecjl);
-            if (threadIdx.x == 0) job.y0_out[item] = a;
-        }
-        if (threadIdx.x == 0 && c.crank == 0 && job.liou_out) job.liou_out[item] = c.n_liou;
-        if (threadIdx.x == 0 && c.crank == 0 && job.n_liou) {
-            job.n_liou[item] = c.n_liou; job.n_lie[item] = c.n_lie; job.n_maps[item] = n_maps;
-            job.n_maps[(size_t)job.n + item] = c.t_conv; job.n_maps[2 * (size_t)job.n + item] = c.t_epi;
-            job.n_maps[3 * (size_t)job.n + item] = clock64() - t_item;
-            job.n_maps[4 * (size_t)job.n + item] = c.t_busy;
-        }
-    }
 }
 
 // ---- small HBM-bound batched operators: one CTA per Hamiltonian, the array streamed in memory order
@@ -496,6 +229,7 @@ struct rg_plan {
     std::vector<void*> owned;  // device allocations
     std::vector<int> w2c;      // wrapped -> centred
     void* kernel = nullptr;
+    int (*upload)(const rgdev::DevPlan*, int) = nullptr;   // into the plan table of the kernel's translation unit
     // staging arena: device memory for host-side arguments of an ABI call.  Grow-only; a call bumps through it, the
     // next call starts from the top again (calls are synchronous), so the steady state has no cudaMalloc/cudaFree.
     std::vector<std::pair<char*, size_t>> arena;   // chunks (more than one only until the next call consolidates them)
@@ -550,24 +284,6 @@ static int dev_upload(rg_plan* p, const T* host, size_t n, T** out) {
     return 0;
 }
 
-typedef void (*kern_t)(const int, const Tables, const Job);
-static kern_t pick_kernel(int J, bool big) {
-    if (big) {
-        switch (J) {
-#define RG_CASE(j) case j: return rg_kernel<j, true>;
-            RG_JBIG_LIST(RG_CASE)
-#undef RG_CASE
-            default: return nullptr;
-        }
-    }
-    switch (J) {
-#define RG_CASE(j) case j: return rg_kernel<j, false>;
-        RG_J_LIST(RG_CASE)
-#undef RG_CASE
-        default: return nullptr;
-    }
-}
-
 // warps per CTA: one lane per output mode -> ceil(M/32) boxes; rounded up to a multiple of 4 so that the four
 // SM sub-partitions carry the same number of warps (14 warps ran 12 % slower than 16: 4+4+3+3), capped at 16
 // (512 threads x 128 registers = the whole register file).
@@ -586,9 +302,6 @@ static size_t smem_bytes(const rgplan::Geometry& g, int n_support, bool big) {
     b += (size_t)g.M * g.JP * 8;
     b += 64 * 8 + 16;            // reduction scratch + work ticket
     b += RG_CTL_UNITS * 16;      // the convolution's control block
-#if defined(RG_SUBTOT_SMEM) && RG_SUBPIECES > 1
-    b += (size_t)12 * g.JP * 32 * 8;   // experiment: per-warp strips of the piece totals behind `out`
-#endif
     return b;
 }
 
@@ -616,9 +329,8 @@ static std::vector<uint16_t> masks_from_iminus(const rgplan::Geometry& g, const 
 extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     if (!prm || !out) return fail(-1, "null argument");
     if (prm->dim < 1 || prm->dim > 3) return fail(-2, "dim must be 1, 2 or 3");
-    if (prm->J < 2 || prm->J > 15) return fail(-2, "J must be in 2..15");
+    if (prm->J < 2 || prm->J > 12) return fail(-2, "J must be in 2..12 (RG.py:61 uses f[2]; beyond 12 the 2(J+1) accumulators of a lane do not fit the register file)");
     if (prm->L < 1 || prm->L > 60) return fail(-2, "L must be in 1..60");
-    if (!pick_kernel(prm->J, false)) return fail(-3, "no kernel compiled for J=" + std::to_string(prm->J) + " (rebuild with -DRG_J_LIST)");
     if (prm->ct < 0 || prm->ct > 2) return fail(-2, "unknown canonical transformation");
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -632,17 +344,15 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, p->device));
     const bool big = needs_global_records(g, mask, (size_t)prop.sharedMemPerBlockOptin);
-    if (big && !pick_kernel(prm->J, true)) {
+    const KernelInst inst = pick_inst(prm->J, big);
+    if (!inst.kernel) {
         delete p;
-        return fail(-3, "Hamiltonian too large for one CTA's shared memory and no global-record kernel compiled for J=" +
-                            std::to_string(prm->J) + " (rebuild with RG_JBIG_LIST)");
+        return fail(-3, std::string("this build of librg_b200.so has no ") + (big ? "global-record " : "") + "kernel for J=" +
+                            std::to_string(prm->J) + " (rg_b200/csrc/Makefile: JS lists the Taylor orders to instantiate)");
     }
     const int n_warps = rg_warps_for(g.M, g.J, big);
     for (int ci = 0; ci < 3; ++ci) {
         int vw = n_warps << ci;   // virtual warps of a cluster of 1, 2, 4 CTAs
-#if RG_VWARPS > 1
-        if (ci == 0) vw *= RG_VWARPS;   // experiment: finer pieces for the one-CTA plans (rg_device.cuh, conv_all)
-#endif
         p->hs[3 * ci + 0] = rgplan::make_schedule(g, mask, false, false, vw, 1 << ci);
         p->hs[3 * ci + 1] = rgplan::make_schedule(g, mask, true, false, vw, 1 << ci);
         p->hs[3 * ci + 2] = rgplan::make_schedule(g, mask, false, true, vw, 1 << ci);
@@ -650,7 +360,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     p->sm_count = prop.multiProcessorCount;
     p->threads = n_warps * 32;
     for (int s = 0; s < 9; ++s)
-        if (p->hs[s].n_warps != (n_warps << (s / 3)) * ((RG_VWARPS > 1 && s < 3) ? RG_VWARPS : 1) || p->hs[s].n_boxes > RG_MAX_BOXES) {
+        if (p->hs[s].n_warps != (n_warps << (s / 3)) || p->hs[s].n_boxes > RG_MAX_BOXES) {
             delete p;
             return fail(-5, "too many output modes for one CTA's convolution schedule");
         }
@@ -738,7 +448,8 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
         dp.sched[s].lane_out = ds.lane_out; dp.sched[s].lane_coord = ds.lane_coord; dp.sched[s].pieces = ds.pieces;
         dp.sched[s].entries = ds.entries; dp.sched[s].supp_rec = ds.supp_rec;
     }
-    p->kernel = (void*)pick_kernel(g.J, big);
+    p->kernel = (void*)inst.kernel;
+    p->upload = inst.upload;
     for (int s = 0; s < 2; ++s) {
         p->smem[s] = smem_bytes(g, p->hs[s].n_support, big);
         if (p->smem[s] > (size_t)prop.sharedMemPerBlockOptin) {
@@ -759,7 +470,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     }
     p->slot = alloc_slot();
     if (p->slot < 0) { rg_plan_destroy(p); return fail(-8, "too many live plans (max " + std::to_string(RG_MAX_PLANS) + " per process)"); }
-    CU(cudaMemcpyToSymbol(c_plan, &p->dp, sizeof(DevPlan), sizeof(DevPlan) * (size_t)p->slot));
+    CU((cudaError_t)p->upload(&p->dp, p->slot));
     // largest cluster the device co-schedules with this kernel's footprint
     p->max_cluster = 1;
     for (int cs = 2; cs <= 4; cs *= 2) {
@@ -919,19 +630,19 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     }
     job.csize = csize;
     int grid = std::max(1, std::min(job.n, p->grid_max[s] / csize)) * csize;
-    kern_t k = (kern_t)p->kernel;
     CU(cudaEventRecord(p->ev0, p->stream));
-    if (csize == 1) {
-        k<<<grid, p->threads, p->smem[s], p->stream>>>(p->slot, T, job);
-    } else {
+    {
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(p->threads); cfg.dynamicSmemBytes = p->smem[s]; cfg.stream = p->stream;
         cudaLaunchAttribute attr;
         attr.id = cudaLaunchAttributeClusterDimension;
         attr.val.clusterDim.x = csize; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-        cfg.attrs = &attr; cfg.numAttrs = 1;
-        CU(cudaLaunchKernelEx(&cfg, k, p->slot, T, job));
+        cfg.attrs = &attr; cfg.numAttrs = csize > 1 ? 1 : 0;
+        int slot = p->slot;
+        Tables Tc = T;
+        void* args[3] = {&slot, &Tc, &job};
+        CU(cudaLaunchKernelExC(&cfg, p->kernel, args));
     }
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev1, p->stream));
@@ -964,12 +675,11 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
 
 extern "C" int rg_region(rg_plan* p, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
                          int32_t* conv, int32_t* count, int32_t* err, rg_stats* stats) {
-    return rg_region_work(p, tab, n, amps, K_flat, nK, conv, count, err, nullptr, 0, 0, stats);
+    return rg_region_work(p, tab, n, amps, K_flat, nK, conv, count, err, nullptr, stats);
 }
 
 extern "C" int rg_region_work(rg_plan* p, const rg_tables* tab, int32_t n, const double* amps, const int32_t* K_flat, int32_t nK,
-                              int32_t* conv, int32_t* count, int32_t* err, int64_t* liouville_per_point,
-                              int32_t row_len, int32_t hot_threshold, rg_stats* stats) {
+                              int32_t* conv, int32_t* count, int32_t* err, int64_t* liouville_per_point, rg_stats* stats) {
     if (!p || !tab || n < 0 || !amps || !K_flat || nK < 1 || !conv || !count || !err) return fail(-1, "bad argument");
     if (p->dp.ct == RG_CT_MULTIPLY && !RG_HAVE_MULTIPLY) return fail(-7, "expm_multiply not available in this build");
     CU(cudaSetDevice(p->device));
@@ -991,15 +701,6 @@ extern "C" int rg_region_work(rg_plan* p, const rg_tables* tab, int32_t n, const
     if ((rc = st.outp(count, sizeof(int) * (size_t)n, &o))) return rc; job.count = (int*)o;
     if ((rc = st.outp(err, sizeof(int) * (size_t)n, &o))) return rc; job.err = (int*)o;
     if (liouville_per_point) { if ((rc = st.outp(liouville_per_point, sizeof(long long) * (size_t)n, &o))) return rc; job.liou_out = (long long*)o; }
-    if (row_len > 0 && n > 0) {
-        // claimed[n] | q_ctr[4] | prio_q[4n], zero-initialised
-        const size_t words = (size_t)n + 4 + 4 * (size_t)n;
-        int* d_sched = nullptr;
-        { void* v; if ((rc = st.dev(sizeof(int) * words, &v))) return rc; d_sched = (int*)v; }
-        CU(cudaMemsetAsync(d_sched, 0, sizeof(int) * words, p->stream));
-        job.claimed = d_sched; job.q_ctr = d_sched + n; job.prio_q = d_sched + n + 4;
-        job.row_len = row_len; job.hot_threshold = hot_threshold > 0 ? hot_threshold : 1500; job.q_cap = 4 * n;
-    }
     if ((rc = launch_job(p, tab->t, job, stats, st))) return rc;
     return st.finish();
 }
@@ -1248,10 +949,6 @@ extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_
     rgplan::Geometry g; g.init(dim, L, J);
     std::vector<uint16_t> mask = masks_from_iminus(g, iminus_wrapped);
     int nw_plan = rg_warps_for(g.M, g.J, needs_global_records(g, mask, RG_SMEM_OPTIN));
-    // RG_B200_VWARPS = 2..4: the plan for that many virtual warps per real warp (elastic helpers);
-    // this debug entry point only -- the kernels run the plan for the real warps
-    const char* vw = getenv("RG_B200_VWARPS");
-    if (vw && atoi(vw) >= 2 && atoi(vw) <= 4) nw_plan *= atoi(vw);
     rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, nw_plan);
     if (s.n_warps < 0) return fail(-5, "too many output modes for one CTA's convolution schedule");
     *n_warps = s.n_warps; *n_boxes = s.n_boxes; *n_entries = (int)s.entries.size() / 2; *n_support = s.n_support;

@@ -66,6 +66,13 @@ enum { WS_FA = 0, WS_FB, WS_Y1, WS_Y2, WS_Y3, WS_H1, WS_H2, WS_T0, WS_T1, WS_T2,
 // its plan by slot.  Shared-memory pointers are always re-derived from the __shared__ symbol so that
 // the compiler emits LDS/STS, never generic loads.
 #define RG_MAX_PLANS 16
+// One plan table per translation unit (= per instantiated kernel), under a name unique to the unit: with internal
+// linkage (`static`) ptxas allocates the hot loop of conv_all differently (82 instead of 90 operand-reuse hits per
+// complete Taylor product at J = 10, +2.5 % kernel time).
+#ifndef RG_PLAN_TABLE
+#define RG_PLAN_TABLE c_plan_host
+#endif
+#define c_plan RG_PLAN_TABLE
 __constant__ DevPlan c_plan[RG_MAX_PLANS];
 extern __shared__ double2 smem_dyn[];
 
@@ -79,10 +86,10 @@ struct Ctx {
     double2* rec; // global operand records (plans with rec_global), else unused
     const double* Omega_nu;  // current Omega.nu, centred, global
     long long n_liou, n_lie;
-    long long budget_base;   // n_liou when the current converge started: max_liouville is a budget per converge (RG.approach runs many)
     uint64_t rng;  // state of the 1-norm estimator's +-1 columns (seeded per Hamiltonian)
     long long t_conv, t_epi;  // SM clocks spent in conv_all / series_epilogue (thread 0's view; profiling aid)
     long long t_busy;         // of t_conv: clocks warp 0 spent computing its own pieces (the rest is barrier wait)
+    long long budget_base;   // n_liou when the current converge started: max_liouville is a budget per converge (RG.approach runs many)
 };
 
 // Shared memory of a CTA: [red: 64 doubles of reduction scratch + 16 bytes for the work ticket | G | Y | out].
@@ -94,26 +101,12 @@ struct Smem {
     double* out;  // [M][JP]
 };
 #define RG_RED_UNITS 33   // 16-byte units of the `red` block
-#define RG_CTL_UNITS 64   // 16-byte units of the convolution's control block: 256 ints (per-box rank counters + 1)
-#define RG_MAX_BOXES 250
+#define RG_CTL_UNITS 128  // 16-byte units of the convolution control block: 512 ints (per-box rank counters + 1)
+#define RG_MAX_BOXES 500
 // An out-of-range lane gathers the zero record whose index is congruent (mod 8) to the record it would have
 // read: a quarter-warp's eight addresses then stay in eight distinct 16-byte bank groups whatever the mix of
 // in-range and out-of-range lanes (with a single zero record 30 % of the shared-memory wavefronts were replays).
 #define RG_ZERO_RECS 8
-#ifdef RG_DBG_BUSY
-// experiment builds: clocks of CTA 0 -- [0..11] busy clocks of its warps in conv_all, [31] = brackets, [16..23] phases
-// of a Lie step as seen by thread 0 (16 generate_y, 17 build_Y + build_G, 18 sym_and_norms, 19 Lie steps)
-__device__ unsigned long long g_dbg_busy[32];
-#define RG_DBG_T0 const long long dbg_t0_ = clock64()
-#define RG_DBG_T1 const long long dbg_t1_ = clock64()
-#define RG_DBG_ADD1(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[slot], (unsigned long long)(clock64() - dbg_t1_)); } while (0)
-#define RG_DBG_ADD(slot) do { if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[slot], (unsigned long long)(clock64() - dbg_t0_)); } while (0)
-#else
-#define RG_DBG_T0
-#define RG_DBG_T1
-#define RG_DBG_ADD1(slot)
-#define RG_DBG_ADD(slot)
-#endif
 __device__ __forceinline__ double* smem_red() { return reinterpret_cast<double*>(smem_dyn); }
 __device__ __forceinline__ int* smem_ctl() { return reinterpret_cast<int*>(smem_dyn + RG_RED_UNITS); }
 template <bool BIG>
@@ -266,7 +259,7 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
 #pragma unroll
     for (int k = 0; k < R::NPAD; ++k) {
         const double2 t = yq[k % R::YW];
-        if (k == 1) decode_entry(q, wn, gp_n, yp_n, jm_n);   // after the first block has issued
+        if (k == (R::NP1 > 1 ? 1 : 0)) decode_entry(q, wn, gp_n, yp_n, jm_n);   // after the first block has issued; before the next record is requested (J = 2: NP1 = 1)
         if (k + R::YW < R::NPAD) yq[k % R::YW] = ldrec<BIG>(q, yp + 16 * R::unit(k + R::YW));
         else yq[k % R::YW] = ldrec<BIG>(q, yp_n + 16 * R::unit(k + R::YW - R::NPAD));
         if (k >= R::NP) continue;   // padding pair
@@ -355,18 +348,6 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     gp = gp_n; yp = yp_n; jm = jm_n;
 }
 
-// RG_SUBPIECES > 1 (experiment for the elastic-helper plan): a piece is summed as RG_SUBPIECES
-// sub-pieces of equal entry count, each from zero, added in order into the piece's running total (registers) while
-// the load pipeline of the stream runs on.  The partial sums then no longer depend on how many warps (or CTAs) share
-// a piece.  (Combining every sub-piece into `out` in (rank, sub-piece) order instead serialises the pieces of a box:
-// measured +42 % / +84 % bracket time with 2 / 4 sub-pieces.)  Measured with the total in registers: +4.8 % kernel
-// time for 2 and for 4 sub-pieces alike (the hot loops' register allocation, not the additions at the marks); with
-// the total in spare shared memory (-DRG_SUBTOT_SMEM) +6.6 % / +9.2 %.  DESIGN.md section 9 weighs this against
-// coarser units.  The
-// default build (RG_SUBPIECES = 1) has no marks and compiles to the SASS it always had.
-#ifndef RG_SUBPIECES
-#define RG_SUBPIECES 1
-#endif
 template <int J, bool BIG>
 __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, int e_end, double (&acc)[J + 1]) {
     typedef RecGeom<J> R;
@@ -411,19 +392,6 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     // dispatch chain per entry.  The outer loop only repeats if a list were not sorted.
     int i = e_begin;
     const int last = e_end - 1;
-#if RG_SUBPIECES > 1
-    const int e_all = e_end;
-#ifdef RG_SUBTOT_SMEM
-    double* const totp = sm.out + (size_t)P.M * (J + 1) + (size_t)(threadIdx.x >> 5) * (J + 1) * 32 + lane;
-#else
-    double tot[J + 1];
-#pragma unroll
-    for (int j = 0; j <= J; ++j) tot[j] = 0.0;
-#endif
-#pragma unroll 1
-    for (int sub = 0; sub < RG_SUBPIECES; ++sub) {
-    e_end = e_begin + ((e_all - e_begin) * (sub + 1)) / RG_SUBPIECES;
-#endif
 #pragma unroll 1
     while (i < e_end) {
 #pragma unroll 1
@@ -451,31 +419,6 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
             wn = wnn; ++i;
         }
     }
-#if RG_SUBPIECES > 1
-    // mark: the sub-piece's sum joins the piece's running total (a fixed two-level tree: sub-pieces in order inside
-    // a piece, pieces in rank order inside a box); the stream's loads run on
-#ifdef RG_SUBTOT_SMEM   // the total lives in the warp's private strip of shared memory behind `out` ([j][lane], conflict free)
-    if (sub == 0 && RG_SUBPIECES > 1) {
-#pragma unroll
-        for (int j = 0; j <= J; ++j) { totp[j * 32] = acc[j]; acc[j] = 0.0; }
-    } else if (sub + 1 < RG_SUBPIECES) {
-#pragma unroll
-        for (int j = 0; j <= J; ++j) { totp[j * 32] += acc[j]; acc[j] = 0.0; }
-    } else {
-#pragma unroll
-        for (int j = 0; j <= J; ++j) acc[j] = totp[j * 32] + acc[j];
-    }
-#else
-    if (sub + 1 < RG_SUBPIECES) {
-#pragma unroll
-        for (int j = 0; j <= J; ++j) { tot[j] += acc[j]; acc[j] = 0.0; }
-    } else {
-#pragma unroll
-        for (int j = 0; j <= J; ++j) acc[j] = tot[j] + acc[j];
-    }
-#endif
-    }
-#endif
 }
 
 // out[nu][j] = conv(dA y, Omega g) - conv(Omega y, dA g)  (G, Y in shared memory).  Ends with a barrier.
@@ -516,30 +459,11 @@ __device__ RG_CONV_ATTR void conv_all(Ctx& c) {
     __syncthreads();
     double acc[JP];
     const long long t_stage = clock64();
-    // RG_VWARPS > 1 (experiment for the elastic-helper plan; compiled out by default): the plan is
-    // dealt to RG_VWARPS virtual warps per real warp -- finer pieces, the unit a helper CTA would take -- and a lone CTA
-    // runs them in rounds, virtual warp vv * (warps of the CTA) + w in round vv.  Interleaved, not blocked: a piece of
-    // rank r waits for the piece of rank r - 1, which belongs to the previous virtual warp, and that one must be running
-    // concurrently or be finished (with blocked rounds every warp would wait for its neighbour's second round).
-#ifndef RG_VWARPS
-#define RG_VWARPS 1
-#endif
-#if RG_VWARPS > 1
-    const int nvirt = max(1, S.n_warps / (nwc * c.csize));
-    if (vw < nwc * c.csize) {
-#else
     if (vw < S.n_warps) {
-#endif
         for (int st = 0; st < S.n_stages; ++st) {
             const int4* pieces = S.pieces + (size_t)st * S.n_warps * S.maxp;
-#if RG_VWARPS > 1
-#pragma unroll 1
-            for (int vv = 0; vv < nvirt; ++vv) {
-            const int pw = c.crank * nwc * nvirt + vv * nwc + w;
-#else
             {
             const int pw = vw;
-#endif
 #pragma unroll 1
             for (int q = 0; q < S.maxp; ++q) {
                 const int4 p = pieces[pw * S.maxp + q];      // heads first, the continuation (if any) last
@@ -572,10 +496,6 @@ __device__ RG_CONV_ATTR void conv_all(Ctx& c) {
         }
     }
     c.t_busy += clock64() - t_stage;
-#ifdef RG_DBG_BUSY
-    if (lane == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[w], (unsigned long long)(clock64() - t_stage));
-    if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[31], 1ull);
-#endif
     __syncthreads();
     if (c.csize > 1) {
         cg::cluster_group cl = cg::this_cluster();
@@ -755,7 +675,7 @@ __device__ __forceinline__ double2 series_epilogue(Ctx& c, double* __restrict__ 
     return series_epilogue_impl<J, BIG, false>(c, f, a0, first, y3mul, y3div, use_div, m);
 }
 
-__device__ __noinline__ void copy_arr(const Ctx& c, double* dst, const double* src) {
+static __device__ __noinline__ void copy_arr(const Ctx& c, double* dst, const double* src) {
     const int n = RG_PLAN(c).vecjl;
     for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
@@ -767,14 +687,11 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
     const double tol = 1.1102230246251565e-16;
     const double a0 = use_div ? a_unscaled / divisor : a_unscaled * step;
     int err = 0;
-    RG_DBG_T1;
     const int sidx_saved = c.sidx;
     if (c.sidx == 0 && c.symm) c.sidx = 2;   // exactly symmetric f and antisymmetric y: compute nu <= 0 only
-    { RG_DBG_T0;
     build_Y<J, BIG>(c, step, divisor, use_div);
     build_G<J, BIG>(c, f);
     __syncthreads();
-    RG_DBG_ADD(17); }
     // one loop for all terms (the first one adds y3 and is not divided): conv_all and the epilogue appear once
     double c1 = 0.0;
     for (int m = 1; m == 1 || m_star <= 0 || m <= m_star; ++m) {
@@ -789,7 +706,6 @@ __device__ __noinline__ int expm_series(Ctx& c, double* f, double a_unscaled, do
         if (m >= P.max_series || c.n_liou - c.budget_base > P.max_liouville) { err = 1; break; }  // safety: the reference would spin (quirk Q6)
     }
     c.sidx = sidx_saved;
-    RG_DBG_ADD1(21);
     return err;
 }
 
@@ -975,19 +891,14 @@ __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, i
     int err = 0, kl = 0;
     double2 nn = sym_and_norms<J>(c, f, false);
     while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie && c.n_liou - c.budget_base <= P.max_liouville) {
-        RG_DBG_T1;
         double a;
-        { RG_DBG_T0; a = generate_y<J>(c, f);
-        __syncthreads(); RG_DBG_ADD(16); }
+        a = generate_y<J>(c, f);
+        __syncthreads();
         if (P.ct == 0) err = expm_onestep<J, BIG>(c, f, a, 1.0);
         else if (P.ct == 1) err = expm_adapt<J, BIG>(c, f, a, 1.0, err);
         else err = expm_multiply<J, BIG>(c, f, a);
-        { RG_DBG_T0; __syncthreads();
-        nn = sym_and_norms<J>(c, f, true); RG_DBG_ADD(18); }
-#ifdef RG_DBG_BUSY
-        if (threadIdx.x == 0 && blockIdx.x == 0) atomicAdd(&g_dbg_busy[19], 1ull);
-#endif
-        RG_DBG_ADD1(20);
+        __syncthreads();
+        nn = sym_and_norms<J>(c, f, true);
         ++kl;
         c.n_lie++;
     }
@@ -1015,6 +926,7 @@ __device__ __forceinline__ int converge_dev(Ctx& c, double*& f, const Tables& T,
         f = rg_map_dev<J, BIG>(c, f, T, k0 + k, err, ni);
         ++k; ++n_maps;
     }
+    if (status == 0 && c.n_liou - c.budget_base > P.max_liouville) status = 2;   // cut short inside the last rg_map
     conv = (ni < P.tol_min) && status == 0;
     return k;
 }

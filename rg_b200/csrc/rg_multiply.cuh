@@ -40,7 +40,7 @@ __device__ __forceinline__ uint64_t splitmix(uint64_t& s) {
     return z ^ (z >> 31);
 }
 // a column of +-1 (np.random.randint(0,2,n)*2-1 in scipy's resample_column); deterministic per (point, draw)
-__device__ __noinline__ void random_signs(const Ctx& c, double* col, uint64_t key, double scale) {
+static __device__ __noinline__ void random_signs(const Ctx& c, double* col, uint64_t key, double scale) {
     const int n = RG_PLAN(c).vecjl;
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         uint64_t s = key + (uint64_t)i * 0xD1B54A32D192ED03ull;
@@ -48,21 +48,21 @@ __device__ __noinline__ void random_signs(const Ctx& c, double* col, uint64_t ke
     }
 }
 // (sum|a|, sum|b|) -- plain sums (the estimator's norms are 1-norms whatever NormChoice is)
-__device__ __noinline__ double2 abs_sums(const Ctx& c, const double* a, const double* b) {
+static __device__ __noinline__ double2 abs_sums(const Ctx& c, const double* a, const double* b) {
     const DevPlan& P = RG_PLAN(c);
     double pa = 0.0, pb = 0.0;
     for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) { pa += fabs(a[i]); pb += fabs(b[i]); }
     return block_reduce2(smem_red(), 0, pa, pb);
 }
 // (a.b, a.d)
-__device__ __noinline__ double2 dots(const Ctx& c, const double* a, const double* b, const double* d) {
+static __device__ __noinline__ double2 dots(const Ctx& c, const double* a, const double* b, const double* d) {
     const DevPlan& P = RG_PLAN(c);
     double pa = 0.0, pb = 0.0;
     for (int i = threadIdx.x; i < P.vecjl; i += blockDim.x) { const double v = a[i]; pa += v * b[i]; pb += v * d[i]; }
     return block_reduce2(smem_red(), 0, pa, pb);
 }
 // arg max of h over indices not in excl[0..n_excl): larger value first, ties -> larger index
-__device__ __noinline__ int block_argmax(const Ctx& c, const double* h, const int* excl, int n_excl, double* vmax) {
+static __device__ __noinline__ int block_argmax(const Ctx& c, const double* h, const int* excl, int n_excl, double* vmax) {
     const DevPlan& P = RG_PLAN(c);
     double* red = smem_red();
     double bv = -1.0; int bi = -1;

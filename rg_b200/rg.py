@@ -231,7 +231,9 @@ class RG:
             prm.n_theta = len(self._theta)
             prm.device = self._device_index()
             prm.max_series = 0
-            prm.max_liouville = int(os.environ.get("RG_B200_MAX_LIOUVILLE", "0"))
+            # work budget per converge (liouville evaluations; 0 = the library default 2e6).  Not a reference key: the
+            # reference has no cap at all (quirk Q6) and spends CPU-days on a few pixels of config 4 with expm_multiply
+            prm.max_liouville = int(getattr(self, "MaxLiouville", 0) or os.environ.get("RG_B200_MAX_LIOUVILLE", "0"))
             h = ctypes.c_void_p()
             _lib.check(L.rg_plan_create(ctypes.byref(prm), ctypes.byref(h)))
             self._plans[name] = h
@@ -610,12 +612,10 @@ class RG:
             out.append(int(k[0]) * self._M + int(xp.ravel_multi_index(tuple(xp.mod(k[1:], n1)), self.r_jl[1:])))
         return xp.array(out, dtype=xp.int32)
 
-    def points(self, amps, conv=None, count=None, err=None, work=None, row_len=0, hot_threshold=0):
+    def points(self, amps, conv=None, count=None, err=None, work=None):
         """`point` for a batch: amps[B, len(K)] (host ndarray, pinned torch tensor or CUDA tensor).
         Returns (conv, count, error) int32 arrays (or fills the supplied host/device buffers).
-        `work`: optional int64[B] buffer receiving the liouville evaluations spent on each point.
-        `row_len` > 0: the batch is a row-major grid with rows of that length; heavy points then pull their
-        grid neighbours forward in the device work queue (load balance only, results are unchanged)."""
+        `work`: optional int64[B] buffer receiving the liouville evaluations spent on each point."""
         if isinstance(amps, xp.ndarray):
             amps = _f64(amps)
             n = amps.shape[0]
@@ -628,5 +628,5 @@ class RG:
         nrm, onu, oms, tab = self._tables(self.Omega)
         kf = self.K_flat()
         _lib.check(_lib.lib().rg_region_work(self._plan(), tab, n, _ptr(amps), kf.ctypes.data, nK, _ptr(conv), _ptr(count),
-                                             _ptr(err), _ptr(work), int(row_len), int(hot_threshold), self._stats()))
+                                             _ptr(err), _ptr(work), self._stats()))
         return conv, count, err

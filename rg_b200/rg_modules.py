@@ -211,9 +211,6 @@ def region_maps(case, x_vec, y_vec):
     n = amps.shape[0]
     rank, world = _dist()
     idx = shard_indices(n, rank, world)
-    # (RG.points(row_len=...) can declare the shard a grid so that heavy points pull their neighbours forward in
-    # the device queue; measured on config 4 it does not shorten the tail -- the heavy points sit on ridges one
-    # to three grid points wide whose neighbours belong to other ranks -- so it stays off by default.)
     conv, count, err = case.points(amps[idx])
     local = xp.stack([conv, count, err], axis=1).astype(xp.int32)
     full = gather_sharded(local, n, rank, world, device=case._device_index())

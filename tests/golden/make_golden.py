@@ -157,6 +157,21 @@ def main(argv):
         ops_fixture("ops_golden_L5J5_b", dict(L=5, J=5), (0.03, 0.05), kmax=3)
         ops_fixture("ops_golden_L10J10", dict(L=10, J=10), (0.01, 0.02), kmax=3)
         ops_fixture("ops_golden_L7J4", dict(L=7, J=4), (0.02, 0.03), kmax=3)
+    if "oddsizes" in what:
+        # any (L, J), not only the four benchmark sizes: two odd ones (RG_dict.py:48-49 leaves both free), operators and
+        # rg_map^k plus a small region map each; and the tau-mean torus of RG_dict.py:36-46 (3-D, N with a 5 in it)
+        ops_fixture("ops_golden_L6J7", dict(L=6, J=7), (0.02, 0.03), kmax=3)
+        ops_fixture("ops_golden_L8J3", dict(L=8, J=3), (0.01, 0.04), kmax=3)
+        ops_fixture("ops_golden_L4J12", dict(L=4, J=12), (0.02, 0.02), kmax=2)
+        for ct in ("expm_onestep", "expm_multiply"):
+            region_fixture("region_L6J7_6x6_" + ct, dict(L=6, J=7, CT=ct), np.linspace(0, 0.06, 6), np.linspace(0.004, 0.08, 6))
+        region_fixture("region_L8J3_6x6_expm_adapt", dict(L=8, J=3, CT="expm_adapt"), np.linspace(0, 0.06, 6), np.linspace(0.004, 0.08, 6))
+        region_fixture("region_L9J2_5x5_expm_onestep", dict(L=9, J=2, CT="expm_onestep"), np.linspace(0.002, 0.06, 5), np.linspace(0.004, 0.08, 5))
+    if "taumean" in what:
+        over = dict(torus="taumean", L=3, J=4, CT="expm_onestep")
+        ops_fixture("ops_taumean_L3J4", over, (3e-4, 2e-3, 0.01), kmax=3, with_multiply=False)
+        # the RG_dict domain AmpInf..AmpSup = [0, 7e-4] x [0, 6e-3] (third amplitude fixed at AmpSup[2] = 0.01, RG_modules.py:122-123)
+        region_fixture("region_taumean_L3J4_5x5_expm_onestep", over, np.linspace(0.0, 7e-4, 5), np.linspace(0.0, 6e-3, 5))
     if "ops3" in what:
         ops_fixture("ops_spiral_L4J4", dict(torus="spiral", L=4, J=4), (0.005, 0.02, 0.1), kmax=2)
     if "region5" in what:

@@ -304,29 +304,6 @@ def test_sass_tune_round_trip(tmp_path):
     assert re.search(r"sass_tune: 0 DFMA retuned", r2.stdout), r2.stdout
 
 
-@pytest.mark.parametrize("vwarps", [2, 4])
-def test_schedule_replay_with_virtual_warps(vwarps, monkeypatch):
-    """The plan for 2 or 4 virtual warps per real warp (finer pieces, the unit an elastic helper would take, DESIGN.md
-    section 9) is a valid plan: replayed in numpy it gives the oracle's bracket, every box still has its head in the
-    storing stage, and it has more, shorter pieces than the plan for the real warps."""
-    g = golden("ops_golden_L5J5")
-    c = ro.OracleRG(ro.default_params(L=5, J=5))
-    c.Omega_nu = g["op_Omega_nu"].copy()
-    base = fetch_schedule(c, 2)
-    monkeypatch.setenv("RG_B200_VWARPS", str(vwarps))
-    sched = fetch_schedule(c, 2)
-    assert sched["nw"] == vwarps * base["nw"]
-    npieces = lambda s: int((s["pieces"][:, 0] >= 0).sum())
-    longest = lambda s: int((s["pieces"][:, 2] - s["pieces"][:, 1]).max())
-    assert npieces(sched) > npieces(base) and longest(sched) < longest(base)
-    got = replay(c, sched, g["op_y1"], g["op_y2"], g["op_g"], g["op_Omega_nu"])
-    want = c.liouville((0.0, g["op_y1"], g["op_y2"], g["op_y3"]), g["op_g"])
-    keep = np.zeros(c.M, dtype=bool)
-    keep[:(c.M + 1) // 2] = True
-    keep = np.roll(keep.reshape(c.dim * (2 * c.L + 1,)), c.dim * (-c.L,), axis=tuple(range(c.dim)))
-    assert relmax(got * keep, want * keep) < 1e-13
-
-
 @pytest.mark.parametrize("dim,L,J", [(1, 3, 2), (1, 20, 4), (2, 2, 3), (2, 4, 6), (2, 6, 5), (2, 9, 4), (3, 2, 2), (3, 3, 4)])
 def test_plans_of_random_supports_cover_every_pair_once(dim, L, J):
     """Planner invariants on geometries and I^- supports it was not tuned for (random supports, partial last boxes of

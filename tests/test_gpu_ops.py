@@ -15,7 +15,9 @@ def make(L, J, ct="expm_onestep", **kw):
     return RG(make_param_dict(L=L, J=J, CanonicalTransformation=ct, SaveData=False, **kw))
 
 
-CASES = [("ops_golden_L5J5", 5, 5), ("ops_golden_L10J10", 10, 10), ("ops_golden_L5J5_b", 5, 5)]
+CASES = [("ops_golden_L5J5", 5, 5), ("ops_golden_L10J10", 10, 10), ("ops_golden_L5J5_b", 5, 5),
+         # any (L, J) the reference accepts (RG_dict.py:48-49): odd J, J < L, the largest compiled J
+         ("ops_golden_L6J7", 6, 7), ("ops_golden_L8J3", 8, 3), ("ops_golden_L4J12", 4, 12)]
 
 
 @pytest.mark.parametrize("name,L,J", CASES)

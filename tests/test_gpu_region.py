@@ -33,19 +33,36 @@ def near_critical(conv):
     return m
 
 
-def check_maps(c, g, near_critical_oracle=None):
+NEAR_CRITICAL_REPORT = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out", "near_critical_pixels.jsonl")
+MAX_NEAR_CRITICAL = 2      # per map: pixels next to the critical surface that may differ from the reference golden
+
+
+def check_maps(c, g, near_critical_oracle=None, label=None):
     """Bit-exact (flag, count, error) maps.  With `near_critical_oracle` (an OracleRG), grid cells adjacent to
     the critical surface may differ from the reference golden -- there the reference's own integer result
     depends on the rounding noise of its FFT convolution -- provided the GPU agrees with the direct-
-    convolution oracle; they are reported separately (BASELINE.json north_star)."""
+    convolution oracle.  BASELINE.json north_star wants them "reported separately": every such pixel is appended
+    to gpurun_out/near_critical_pixels.jsonl (copied to profiles/ after a GPU run) and their number per map is
+    bounded by MAX_NEAR_CRITICAL."""
+    import json
     conv, count, err = run_region(c, g)
     bad = (conv != g["conv"]) | (count != g["count"]) | (err != g["error"])
     if near_critical_oracle is not None and bad.any():
         assert (bad & ~near_critical(g["conv"])).sum() == 0, ("mismatch away from the critical surface", np.argwhere(bad).tolist())
+        assert int(bad.sum()) <= MAX_NEAR_CRITICAL, ("too many near-critical mismatches", np.argwhere(bad).tolist())
         pts = [(g["xs"][ix], g["ys"][iy]) for iy, ix in np.argwhere(bad)]
         oc, on, oe, _ = near_critical_oracle.points(pts)
         got = [(int(conv[iy, ix]), int(count[iy, ix]), int(err[iy, ix])) for iy, ix in np.argwhere(bad)]
         assert got == [(int(a), int(b), int(e)) for a, b, e in zip(oc, on, oe)], ("GPU differs from the oracle", got)
+        try:
+            os.makedirs(os.path.dirname(NEAR_CRITICAL_REPORT), exist_ok=True)
+            with open(NEAR_CRITICAL_REPORT, "a") as fh:
+                for (iy, ix), gq in zip(np.argwhere(bad), got):
+                    fh.write(json.dumps({"map": label or os.environ.get("PYTEST_CURRENT_TEST", "?"), "iy": int(iy), "ix": int(ix),
+                                         "x": float(g["xs"][ix]), "y": float(g["ys"][iy]), "gpu_and_oracle": gq,
+                                         "reference": [int(g["conv"][iy, ix]), int(g["count"][iy, ix]), int(g["error"][iy, ix])]}) + "\n")
+        except OSError:
+            pass
         print("near-critical points reported separately:", np.argwhere(bad).tolist(), "gpu/oracle", got,
               "reference", g["count"][bad].tolist())
     else:
@@ -97,6 +114,98 @@ def test_region_L10J10_heavy_grid():
     c.close()
 
 
+@pytest.mark.parametrize("name,L,J,ct", [("region_L6J7_6x6_expm_onestep", 6, 7, "expm_onestep"),
+                                         ("region_L6J7_6x6_expm_multiply", 6, 7, "expm_multiply"),
+                                         ("region_L8J3_6x6_expm_adapt", 8, 3, "expm_adapt"),
+                                         ("region_L9J2_5x5_expm_onestep", 9, 2, "expm_onestep")])
+def test_region_odd_sizes(name, L, J, ct):
+    """Any (L, J) (RG_dict.py:48-49): a kernel is instantiated for every Taylor order 2..12.  Maps frozen from the
+    live reference at sizes outside the benchmark set."""
+    import rg_oracle as ro
+    g = golden(name)
+    c = make(L, J, ct)
+    check_maps(c, g, near_critical_oracle=ro.OracleRG(ro.default_params(L=L, J=J, CT=ct)))
+    c.close()
+
+
+@pytest.mark.parametrize("J", [2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12])
+def test_every_taylor_order_has_a_kernel(J):
+    """A 3x3 region map at L = 4 for every compiled Taylor order, both record placements (shared memory and the
+    global-record BIG variant), against the CPU oracle."""
+    import rg_oracle as ro
+    from rg_b200.rg_modules import region_maps
+    xs, ys = np.linspace(0.004, 0.05, 3), np.linspace(0.006, 0.07, 3)
+    orc = ro.OracleRG(ro.default_params(L=4, J=J, CT="expm_onestep"))
+    oc, on, oe, _ = orc.region(xs, ys)
+    for big in ("0", "1"):
+        os.environ["RG_B200_FORCE_GLOBAL"] = big
+        try:
+            c = make(4, J, "expm_onestep")
+            data, info = region_maps(c, xs, ys)
+            assert np.array_equal(data[:, :, 0], oc) and np.array_equal(data[:, :, 1], on) and np.array_equal(info, oe), (J, big)
+            c.close()
+        finally:
+            os.environ.pop("RG_B200_FORCE_GLOBAL", None)
+
+
+def test_J_out_of_range_is_rejected():
+    from rg_b200 import _lib
+    for J in (1, 13):
+        c = make(4, J, "expm_onestep")
+        with pytest.raises((_lib.RGError, Exception)):
+            c.plan_info()
+
+
+def test_region_taumean_L3J4():
+    """The third torus of RG_dict.py (tau mean, RG_dict.py:36-46: n = 3, N = [[0,1,-1],[1,-1,1],[0,-1,2]], negative
+    entries in K): 5x5 map frozen from the live reference."""
+    import rg_oracle as ro
+    from rg_b200 import RG, make_param_dict
+    from rg_b200.rg_dict import TAU_MEAN
+    g = golden("region_taumean_L3J4_5x5_expm_onestep")
+    c = RG(make_param_dict(L=3, J=4, CanonicalTransformation="expm_onestep", SaveData=False, **TAU_MEAN))
+    check_maps(c, g, near_critical_oracle=ro.OracleRG(ro.default_params(L=3, J=4, CT="expm_onestep", torus="taumean")))
+    c.close()
+
+
+def test_heavy_multiply_pixels_config4():
+    """Pixels of BASELINE config 4 that are very expensive with expm_multiply (RG_dict's default transformation):
+    compute_m_s returns s ~ 1e4..1e5 on a Hamiltonian about to diverge, so the reference spends 1e5 - 4e5 liouville
+    evaluations (5 - 30 CPU-minutes) on each.  Frozen from the live reference (tests/golden/make_heavy_multiply.py);
+    the GPU must give the same (flag, count, error) with the work budget lifted, in a comparable number of
+    evaluations (the 1-norm estimates differ with the RNG stream, quirk Q7)."""
+    import json
+    path = os.path.join(GOLDEN, "heavy_multiply_L10J10.jsonl")
+    rows = [json.loads(l) for l in open(path) if l.strip()]
+    assert len(rows) >= 2
+    os.environ["RG_B200_MAX_LIOUVILLE"] = "20000000"
+    try:
+        c = make(10, 10, "expm_multiply", AmpInf=[0.0, 0.0], AmpSup=[0.12, 0.35])
+        amps = np.array([[r["x"], r["y"]] for r in rows])
+        work = np.zeros(len(rows), np.int64)
+        conv, count, err = c.points(amps, work=work)
+        for r, cv, cn, e, w in zip(rows, conv, count, err, work):
+            assert (int(cv), int(cn), int(e)) == (r["conv"], r["count"], r["error"]), (r, cv, cn, e)
+            assert 0.5 * r["liouvilles"] <= w <= 2.0 * r["liouvilles"], (r, w)
+        c.close()
+    finally:
+        os.environ.pop("RG_B200_MAX_LIOUVILLE", None)
+
+
+def test_work_budget_is_reported_not_disguised():
+    """A Hamiltonian cut short by the work budget comes back as RG_ERR_WORK_BUDGET (-98), never as a result: the pixel
+    (x = 0, iy = 110 of config 4) needs > 6e6 liouville evaluations with expm_multiply."""
+    os.environ["RG_B200_MAX_LIOUVILLE"] = "20000"
+    try:
+        c = make(10, 10, "expm_multiply", AmpInf=[0.0, 0.0], AmpSup=[0.12, 0.35])
+        y = np.linspace(0, 0.35, 256)[110]
+        conv, count, err = c.points(np.array([[0.0, y]]))
+        assert int(err[0]) == -98 and int(conv[0]) == 0
+        c.close()
+    finally:
+        os.environ.pop("RG_B200_MAX_LIOUVILLE", None)
+
+
 def test_region_spiral_L4J4():
     """n = 3 (spiral mean), L=J=4: the same kernels with three Fourier axes."""
     from rg_b200 import RG, make_param_dict
@@ -117,7 +226,7 @@ def test_global_record_kernel_matches_shared(monkeypatch):
     c0 = RG(p)
     h = c0.generate_1Hamiltonian([0.01, 0.05, 0.02], symmetric=True)
     f_small = c0.rg_map(c0.rg_map(h)).f
-    assert c0.plan_info()["smem_bytes"] > 100000
+    assert c0.plan_info()["smem_bytes"] > 50000       # the shared-memory kernel (operand records on chip)
     c0.close()
     monkeypatch.setenv("RG_B200_FORCE_GLOBAL", "1")
     c1 = RG(p)
