@@ -85,6 +85,7 @@ typedef struct {
     int64_t clk_conv_busy;     /* of clk_conv: clocks warp 0 spent on its own pieces (the rest is barrier wait) */
     float kernel_ms;           /* device time of the last batched call (CUDA events on the plan's stream) */
     int32_t launches;          /* kernels launched by the last call */
+    int64_t liouville_full;    /* of `liouville`: evaluations on the full (not half-space) schedule, e.g. the 1-norm estimator's */
 } rg_stats;
 
 const char* rg_last_error(void);

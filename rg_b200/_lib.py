@@ -35,7 +35,7 @@ class RGStats(ctypes.Structure):
                 ("conv_fma_executed", ctypes.c_int64), ("conv_fma_useful", ctypes.c_int64),
                 ("clk_conv", ctypes.c_int64), ("clk_epilogue", ctypes.c_int64), ("clk_total", ctypes.c_int64),
                 ("clk_conv_busy", ctypes.c_int64),
-                ("kernel_ms", ctypes.c_float), ("launches", ctypes.c_int32)]
+                ("kernel_ms", ctypes.c_float), ("launches", ctypes.c_int32), ("liouville_full", ctypes.c_int64)]
 
 
 # every symbol include/rg_b200.h declares, with its ctypes signature

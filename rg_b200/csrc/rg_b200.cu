@@ -297,9 +297,10 @@ static int rg_warps_for(int M, int J, bool big = false) {
     return w;
 }
 
-static size_t smem_bytes(const rgplan::Geometry& g, int n_support, bool big) {
+static size_t smem_bytes(const rgplan::Geometry& g, int n_support, bool big, bool with_f = false) {
     size_t b = big ? 0 : (size_t)(g.M + RG_ZERO_RECS + n_support) * g.rec_units * 16;
     b += (size_t)g.M * g.JP * 8;
+    if (with_f) b += (size_t)g.vecjl * 8;   // the coefficient array f itself
     b += 64 * 8 + 16;            // reduction scratch + work ticket
     b += RG_CTL_UNITS * 16;      // the convolution's control block
     return b;
@@ -452,6 +453,15 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     p->upload = inst.upload;
     for (int s = 0; s < 2; ++s) {
         p->smem[s] = smem_bytes(g, p->hs[s].n_support, big);
+        // f in shared memory when it does not cost residency: one CTA per SM (J >= 8, BIG) if it fits at all, else
+        // only while four CTAs of the smaller kernels still fit an SM
+        const size_t with_f = smem_bytes(g, p->hs[s].n_support, big, true);
+        const bool one_cta = (g.J >= 8 || big);
+        const char* fe = getenv("RG_B200_F_SMEM");
+        if ((!fe || atoi(fe)) && with_f <= (size_t)prop.sharedMemPerBlockOptin && (one_cta || with_f * 4 + 4096 <= (size_t)prop.sharedMemPerMultiprocessor)) {
+            p->smem[s] = with_f;
+            dp.f_smem |= 1 << s;
+        }
         if (p->smem[s] > (size_t)prop.sharedMemPerBlockOptin) {
             if (s == 0) { rg_plan_destroy(p); return fail(-5, "Hamiltonian too large for one CTA's shared memory (" + std::to_string(p->smem[s]) + " B)"); }
             p->ctas_per_sm[s] = 0; p->grid_max[s] = 0;
@@ -612,8 +622,8 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     const rgplan::Geometry& g = p->g;
     long long* d_cnt = nullptr;
     if (stats) {
-        { void* v; int rc = st.dev(sizeof(long long) * 7 * (size_t)std::max(job.n, 1), &v); if (rc) return rc; d_cnt = (long long*)v; }
-        CU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 7 * (size_t)std::max(job.n, 1), p->stream));
+        { void* v; int rc = st.dev(sizeof(long long) * 8 * (size_t)std::max(job.n, 1), &v); if (rc) return rc; d_cnt = (long long*)v; }
+        CU(cudaMemsetAsync(d_cnt, 0, sizeof(long long) * 8 * (size_t)std::max(job.n, 1), p->stream));
         job.n_liou = d_cnt; job.n_lie = d_cnt + job.n; job.n_maps = d_cnt + 2 * (size_t)job.n;
     }
     CU(cudaMemsetAsync(p->ticket, 0, sizeof(int), p->stream));
@@ -647,7 +657,7 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
     CU(cudaGetLastError());
     CU(cudaEventRecord(p->ev1, p->stream));
     if (stats) {
-        std::vector<long long> h(7 * (size_t)std::max(job.n, 1));
+        std::vector<long long> h(8 * (size_t)std::max(job.n, 1));
         CU(cudaMemcpyAsync(h.data(), d_cnt, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost, p->stream));
         CU(cudaStreamSynchronize(p->stream));
         memset(stats, 0, sizeof(*stats));
@@ -656,12 +666,19 @@ static int launch_job(rg_plan* p, const Tables& T, Job& job, rg_stats* stats, St
             stats->clk_conv += h[3 * (size_t)job.n + i]; stats->clk_epilogue += h[4 * (size_t)job.n + i];
             stats->clk_total += h[5 * (size_t)job.n + i];
             stats->clk_conv_busy += h[6 * (size_t)job.n + i];
+            stats->liouville_full += h[7 * (size_t)job.n + i];
         }
-        // fused modes run the half-space schedule for the series (the 1-norm estimator of expm_multiply runs
-        // the full one; its share is accounted at the half-space cost, i.e. under-counted)
-        const int sa = (s == 0) ? 2 : s;
-        stats->conv_fma_executed = stats->liouville * p->hs[sa].fma_executed;
-        stats->conv_fma_useful = stats->liouville * p->hs[sa].fma_useful;
+        // fused modes run the half-space schedule for the series terms (exactly symmetric operands) and the full one
+        // for everything else (the 1-norm estimator's probes of expm_multiply, asymmetric inputs): each bracket is
+        // accounted at the cost of the schedule it ran on
+        if (s == 0) {
+            const long long half = stats->liouville - stats->liouville_full;
+            stats->conv_fma_executed = half * p->hs[2].fma_executed + stats->liouville_full * p->hs[0].fma_executed;
+            stats->conv_fma_useful = half * p->hs[2].fma_useful + stats->liouville_full * p->hs[0].fma_useful;
+        } else {
+            stats->conv_fma_executed = stats->liouville * p->hs[s].fma_executed;
+            stats->conv_fma_useful = stats->liouville * p->hs[s].fma_useful;
+        }
         CU(cudaEventElapsedTime(&stats->kernel_ms, p->ev0, p->ev1));
         stats->launches = 1;
     }

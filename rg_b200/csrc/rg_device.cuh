@@ -35,6 +35,7 @@ struct DevPlan {
     int max_series;
     long long max_liouville;   // work budget per Hamiltonian (the reference has none, quirk Q6)
     int sym_tables;            // 1: mask[-nu] == mask[nu], omega0_nu[-nu] == -omega0_nu[nu] exactly (checked by the host)
+    int f_smem;                // bit s: launches with schedule kind s keep the coefficient array f in shared memory (behind `out`)
     int rec_global;            // 1: the operand records live in the CTA's global workspace (array too large for shared memory)
     long long ws_stride;       // doubles of workspace per CTA (WS_COUNT arrays + the global records, if any); even
     long long rec_offset;      // doubles from a CTA's workspace base to its global records (16-byte aligned)
@@ -83,9 +84,11 @@ struct Ctx {
     int cbase;    // 3*log2(cluster size): offset of the schedule set
     int csize, crank;  // thread-block cluster size (1, 2, 4) and this CTA's rank in it
     double* ws;   // this CTA's global workspace
+    double* fa;   // home of the coefficient array f: shared memory when it fits (DevPlan::f_smem), else WS_FA
     double2* rec; // global operand records (plans with rec_global), else unused
     const double* Omega_nu;  // current Omega.nu, centred, global
     long long n_liou, n_lie;
+    long long n_liou_full;   // of n_liou: brackets evaluated on the full (not half-space) schedule: the 1-norm estimator's probes
     uint64_t rng;  // state of the 1-norm estimator's +-1 columns (seeded per Hamiltonian)
     long long t_conv, t_epi;  // SM clocks spent in conv_all / series_epilogue (thread 0's view; profiling aid)
     long long t_busy;         // of t_conv: clocks warp 0 spent computing its own pieces (the rest is barrier wait)
@@ -515,6 +518,7 @@ __device__ RG_CONV_ATTR void conv_all(Ctx& c) {
         cl.sync();
     }
     c.n_liou++;
+    if (S.half == 0) c.n_liou_full++;
     c.t_conv += clock64() - t_begin;
 }
 
@@ -884,10 +888,19 @@ __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, i
     const DevPlan& P = RG_PLAN(c);
     double* fa = c.ws + (size_t)WS_FA * P.vecjl;
     double* fb = c.ws + (size_t)WS_FB * P.vecjl;
-    double* dst = (f == fa) ? fb : fa;
     c.Omega_nu = T.Omega_nu + (size_t)(k + 1) * P.M;
-    reindex_rescale<J>(c, f, dst, T.nrm[k]);
-    f = dst;
+    if (c.fa != fa) {
+        // f lives in shared memory: re-index through the global scratch and bring the result home (one extra pass
+        // per rg_map, against ~90 Lie steps whose every term reads and writes f)
+        reindex_rescale<J>(c, f, fb, T.nrm[k]);
+        copy_arr(c, c.fa, fb);
+        __syncthreads();
+        f = c.fa;
+    } else {
+        double* dst = (f == fa) ? fb : fa;
+        reindex_rescale<J>(c, f, dst, T.nrm[k]);
+        f = dst;
+    }
     int err = 0, kl = 0;
     double2 nn = sym_and_norms<J>(c, f, false);
     while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie && c.n_liou - c.budget_base <= P.max_liouville) {

@@ -72,7 +72,9 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
         const int nd2 = (P.M + RG_ZERO_RECS + (BIG ? P.M : RG_SCHED(c).n_support)) * P.rec_units;
         for (int i = threadIdx.x; i < nd2; i += blockDim.x) sm.G[i] = make_double2(0.0, 0.0);
     }
-    double* fa = c.ws + (size_t)WS_FA * P.vecjl;
+    // the coefficient array: in shared memory behind `out` when the plan says it fits for this schedule kind
+    double* fa = ((P.f_smem >> job.sched) & 1) ? sm.out + (size_t)P.M * P.JP : c.ws + (size_t)WS_FA * P.vecjl;
+    c.fa = fa;
     const int M = P.M, c0 = (M - 1) / 2;
     for (;;) {
         if (c.csize > 1) {
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
         }
         const int item = *sh_item;
         if (item >= job.n) break;
-        c.n_liou = 0; c.n_lie = 0; c.budget_base = 0; c.symm = 0; c.t_conv = 0; c.t_epi = 0; c.t_busy = 0;
+        c.n_liou = 0; c.n_liou_full = 0; c.n_lie = 0; c.budget_base = 0; c.symm = 0; c.t_conv = 0; c.t_epi = 0; c.t_busy = 0;
         const long long t_item = clock64();
         c.rng = 0x243F6A8885A308D3ull ^ ((uint64_t)(item + 1) * 0x9E3779B97F4A7C15ull);
         long long n_maps = 0;
@@ -241,6 +243,7 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
             job.n_maps[(size_t)job.n + item] = c.t_conv; job.n_maps[2 * (size_t)job.n + item] = c.t_epi;
             job.n_maps[3 * (size_t)job.n + item] = clock64() - t_item;
             job.n_maps[4 * (size_t)job.n + item] = c.t_busy;
+            job.n_maps[5 * (size_t)job.n + item] = c.n_liou_full;
         }
     }
 }
