@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(256) conv_kernel(const DevPlan P, int n, const
 
 // ------------------------------------------------------------------------------------------------ host runtime
 struct DevSched {
-    int* lane_out = nullptr; uint32_t* lane_coord = nullptr; int4* pieces = nullptr; uint2* entries = nullptr; int* supp_rec = nullptr;
+    int* lane_out = nullptr; uint32_t* lane_coord = nullptr; int4* pieces = nullptr; int2* piece_runs = nullptr; uint2* entries = nullptr; int* supp_rec = nullptr;
 };
 
 struct rg_plan {
@@ -297,10 +297,13 @@ static int rg_warps_for(int M, int J, bool big = false) {
     return w;
 }
 
-static size_t smem_bytes(const rgplan::Geometry& g, int n_support, bool big, bool with_f = false) {
-    size_t b = big ? 0 : (size_t)(g.M + RG_ZERO_RECS + n_support) * g.rec_units * 16;
-    b += (size_t)g.M * g.JP * 8;
-    if (with_f) b += (size_t)g.vecjl * 8;   // the coefficient array f itself
+// Shared memory of one CTA.  Small kernels: two-derivative records of g and y plus `out`.  BIG kernels (product-rule
+// form): the g-only records when they fit (g_smem), else `out`.
+static size_t smem_bytes(const rgplan::Geometry& g, int n_support, bool big, bool g_smem = false) {
+    size_t b;
+    if (!big) b = (size_t)(g.M + RG_ZERO_RECS + n_support) * g.rec_units * 16 + (size_t)g.M * g.JP * 8;
+    else if (g_smem) b = (size_t)(g.M + RG_ZERO_RECS) * g.g_units * 16;
+    else b = (size_t)g.M * g.JP * 8;
     b += 64 * 8 + 16;            // reduction scratch + work ticket
     b += RG_CTL_UNITS * 16;      // the convolution's control block
     return b;
@@ -345,6 +348,9 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, p->device));
     const bool big = needs_global_records(g, mask, (size_t)prop.sharedMemPerBlockOptin);
+    // BIG kernels: the g-only records of the product-rule form go to shared memory when they fit one SM
+    const char* gse = getenv("RG_B200_G_SMEM");
+    const bool g_smem = big && (!gse || atoi(gse)) && smem_bytes(g, 0, true, true) <= (size_t)prop.sharedMemPerBlockOptin;
     const KernelInst inst = pick_inst(prm->J, big);
     if (!inst.kernel) {
         delete p;
@@ -354,9 +360,9 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     const int n_warps = rg_warps_for(g.M, g.J, big);
     for (int ci = 0; ci < 3; ++ci) {
         int vw = n_warps << ci;   // virtual warps of a cluster of 1, 2, 4 CTAs
-        p->hs[3 * ci + 0] = rgplan::make_schedule(g, mask, false, false, vw, 1 << ci);
-        p->hs[3 * ci + 1] = rgplan::make_schedule(g, mask, true, false, vw, 1 << ci);
-        p->hs[3 * ci + 2] = rgplan::make_schedule(g, mask, false, true, vw, 1 << ci);
+        p->hs[3 * ci + 0] = rgplan::make_schedule(g, mask, false, false, vw, 1 << ci, big);
+        p->hs[3 * ci + 1] = rgplan::make_schedule(g, mask, true, false, vw, 1 << ci, big);
+        p->hs[3 * ci + 2] = rgplan::make_schedule(g, mask, false, true, vw, 1 << ci, big);
     }
     p->sm_count = prop.multiProcessorCount;
     p->threads = n_warps * 32;
@@ -369,6 +375,7 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
     memset(&dp, 0, sizeof(dp));
     dp.dim = g.dim; dp.L = g.L; dp.J = g.J; dp.JP = g.JP; dp.n1 = g.n1; dp.M = g.M; dp.vecjl = g.vecjl;
     dp.off2 = g.off2; dp.rec_units = g.rec_units;
+    dp.g_units = big ? g.g_units : g.rec_units; dp.g_smem = g_smem ? 1 : 0;
     dp.idx_y1J = (g.J & 1) ? g.J : g.off2 + g.JP;
     dp.stride0 = g.stride[0]; dp.stride1 = g.stride[1]; dp.stride2 = g.stride[2];
     dp.norm_choice = prm->norm_choice; dp.norm_analytic = prm->norm_analytic;
@@ -386,7 +393,9 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
         dp.sym_tables = ok ? 1 : 0;
     }
     dp.rec_offset = ((long long)WS_COUNT * g.vecjl + 1) & ~1LL;   // records are read as double2: keep them 16-byte aligned
-    dp.ws_stride = dp.rec_offset + (big ? (long long)(2 * g.M + RG_ZERO_RECS) * g.rec_units * 2 : 0LL);
+    // BIG kernels: [Y records: M x rec_units] then [g records: (M + 8) x g_units, or `out`: M x JP doubles when the g records are on chip]
+    dp.rec2_offset = dp.rec_offset + (big ? (long long)g.M * g.rec_units * 2 : 0LL);
+    dp.ws_stride = dp.rec2_offset + (big ? (g_smem ? (((long long)g.M * g.JP + 1) & ~1LL) : (long long)(g.M + RG_ZERO_RECS) * g.g_units * 2) : 0LL);
     dp.debug = getenv("RG_B200_DEBUG") ? atoi(getenv("RG_B200_DEBUG")) : 0;
     // centred tables
     std::vector<double> om0(g.M), normw(g.M);
@@ -437,31 +446,24 @@ extern "C" int rg_plan_create(const rg_params* prm, rg_plan** out) {
         if ((rc = dev_upload(p, hs.lane_out.data(), hs.lane_out.size(), &ds.lane_out))) return rc;
         if ((rc = dev_upload(p, hs.lane_coord.data(), hs.lane_coord.size(), &ds.lane_coord))) return rc;
         if ((rc = dev_upload(p, reinterpret_cast<const int4*>(hs.pieces.data()), hs.pieces.size(), &ds.pieces))) return rc;
+        if ((rc = dev_upload(p, reinterpret_cast<const int2*>(hs.piece_runs.data()), hs.piece_runs.size() / 2, &ds.piece_runs))) return rc;
         if ((rc = dev_upload(p, reinterpret_cast<const uint2*>(hs.entries.data()), hs.entries.size() / 2, &ds.entries))) return rc;
         if ((rc = dev_upload(p, hs.supp_rec.data(), hs.supp_rec.size(), &ds.supp_rec))) return rc;
         dp.sched[s].n_warps = hs.n_warps; dp.sched[s].n_support = hs.n_support;
         dp.sched[s].maxp = hs.maxp;
+        dp.sched[s].general = hs.general ? 1 : 0;
         dp.sched[s].n_boxes = hs.n_boxes; dp.sched[s].half = hs.half ? 1 : 0; dp.sched[s].n_stages = hs.n_stages;
         for (int r = 0; r < 4; ++r) {
             dp.sched[s].fin_begin[r] = hs.fin_begin[r]; dp.sched[s].fin_end[r] = hs.fin_end[r];
             dp.sched[s].stage0_pieces[r] = hs.stage0_pieces[r];
         }
-        dp.sched[s].lane_out = ds.lane_out; dp.sched[s].lane_coord = ds.lane_coord; dp.sched[s].pieces = ds.pieces;
+        dp.sched[s].lane_out = ds.lane_out; dp.sched[s].lane_coord = ds.lane_coord; dp.sched[s].pieces = ds.pieces; dp.sched[s].piece_runs = ds.piece_runs;
         dp.sched[s].entries = ds.entries; dp.sched[s].supp_rec = ds.supp_rec;
     }
     p->kernel = (void*)inst.kernel;
     p->upload = inst.upload;
     for (int s = 0; s < 2; ++s) {
-        p->smem[s] = smem_bytes(g, p->hs[s].n_support, big);
-        // f in shared memory when it does not cost residency: one CTA per SM (J >= 8, BIG) if it fits at all, else
-        // only while four CTAs of the smaller kernels still fit an SM
-        const size_t with_f = smem_bytes(g, p->hs[s].n_support, big, true);
-        const bool one_cta = (g.J >= 8 || big);
-        const char* fe = getenv("RG_B200_F_SMEM");
-        if ((!fe || atoi(fe)) && with_f <= (size_t)prop.sharedMemPerBlockOptin && (one_cta || with_f * 4 + 4096 <= (size_t)prop.sharedMemPerMultiprocessor)) {
-            p->smem[s] = with_f;
-            dp.f_smem |= 1 << s;
-        }
+        p->smem[s] = smem_bytes(g, p->hs[s].n_support, big, g_smem);
         if (p->smem[s] > (size_t)prop.sharedMemPerBlockOptin) {
             if (s == 0) { rg_plan_destroy(p); return fail(-5, "Hamiltonian too large for one CTA's shared memory (" + std::to_string(p->smem[s]) + " B)"); }
             p->ctas_per_sm[s] = 0; p->grid_max[s] = 0;
@@ -965,8 +967,9 @@ extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_
     if (dim < 1 || dim > 3 || J < 1 || J > 15 || L < 1) return fail(-2, "bad geometry");
     rgplan::Geometry g; g.init(dim, L, J);
     std::vector<uint16_t> mask = masks_from_iminus(g, iminus_wrapped);
-    int nw_plan = rg_warps_for(g.M, g.J, needs_global_records(g, mask, RG_SMEM_OPTIN));
-    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, nw_plan);
+    const bool big = needs_global_records(g, mask, RG_SMEM_OPTIN);
+    int nw_plan = rg_warps_for(g.M, g.J, big);
+    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, nw_plan, 1, big);
     if (s.n_warps < 0) return fail(-5, "too many output modes for one CTA's convolution schedule");
     *n_warps = s.n_warps; *n_boxes = s.n_boxes; *n_entries = (int)s.entries.size() / 2; *n_support = s.n_support;
     if (cost) { cost[0] = s.fma_useful; cost[1] = s.fma_executed; cost[2] = s.cost_max; cost[3] = s.cost_total; }

@@ -14,18 +14,22 @@ namespace rgdev {
 
 struct Sched {
     int n_warps, n_boxes, n_support, half, n_stages;
+    int general;                    // 1: caller-supplied generator (schedule kind 1): no product-rule split (BIG kernels)
     int maxp;                       // piece slots per warp and stage (rgplan::Schedule::maxp)
     int fin_begin[4], fin_end[4];   // boxes owned by each CTA of a cluster
     int stage0_pieces[4];           // pieces each CTA combines in the storing stage
     const int* lane_out;         // [NB*32] centred mode of each lane, -1 idle
     const uint32_t* lane_coord;  // [NB*32] packed biased coords
     const int4* pieces;          // [n_stages][NW*maxp] {box, begin, end, rank}; box = -1 unused; heads first
+    const int2* piece_runs;      // same shape: {end of the piece's run of complete products, end of its run truncated to LIM_B}
     const uint2* entries;        // {packed coords of nu1, (rec<<8)|jm}
     const int* supp_rec;         // [M] record of centred mode or -1
 };
 
 struct DevPlan {
     int dim, L, J, JP, n1, M, vecjl, off2, rec_units, idx_y1J;
+    int g_units;               // BIG kernels: 16-byte units of a g record (g[0..J] only, product-rule form); else = rec_units
+    int g_smem;                // BIG kernels: 1 = the g records live in shared memory (and `out` in the global workspace), 0 = in the workspace
     int stride0, stride1, stride2;
     int norm_choice;
     double norm_analytic;
@@ -35,10 +39,10 @@ struct DevPlan {
     int max_series;
     long long max_liouville;   // work budget per Hamiltonian (the reference has none, quirk Q6)
     int sym_tables;            // 1: mask[-nu] == mask[nu], omega0_nu[-nu] == -omega0_nu[nu] exactly (checked by the host)
-    int f_smem;                // bit s: launches with schedule kind s keep the coefficient array f in shared memory (behind `out`)
     int rec_global;            // 1: the operand records live in the CTA's global workspace (array too large for shared memory)
     long long ws_stride;       // doubles of workspace per CTA (WS_COUNT arrays + the global records, if any); even
-    long long rec_offset;      // doubles from a CTA's workspace base to its global records (16-byte aligned)
+    long long rec_offset;      // doubles from a CTA's workspace base to its global records (16-byte aligned): Y records first
+    long long rec2_offset;     // BIG kernels: doubles to the second global block -- the g records (g_smem = 0) or `out` (g_smem = 1)
     int debug;   // RG_B200_DEBUG experiments (0 in production): bit0 gather always hits the zero record,
                  // bit1 every entry broadcasts y record 0
     const double* omega0_nu;  // [M] centred
@@ -84,8 +88,8 @@ struct Ctx {
     int cbase;    // 3*log2(cluster size): offset of the schedule set
     int csize, crank;  // thread-block cluster size (1, 2, 4) and this CTA's rank in it
     double* ws;   // this CTA's global workspace
-    double* fa;   // home of the coefficient array f: shared memory when it fits (DevPlan::f_smem), else WS_FA
-    double2* rec; // global operand records (plans with rec_global), else unused
+    double2* rec; // global operand records (BIG kernels): the Y records
+    double* rec2; // BIG kernels: the g records (g_smem = 0) or `out` (g_smem = 1) in the global workspace
     const double* Omega_nu;  // current Omega.nu, centred, global
     long long n_liou, n_lie;
     long long n_liou_full;   // of n_liou: brackets evaluated on the full (not half-space) schedule: the 1-norm estimator's probes
@@ -112,13 +116,23 @@ struct Smem {
 #define RG_ZERO_RECS 8
 __device__ __forceinline__ double* smem_red() { return reinterpret_cast<double*>(smem_dyn); }
 __device__ __forceinline__ int* smem_ctl() { return reinterpret_cast<int*>(smem_dyn + RG_RED_UNITS); }
+// BIG kernels (Hamiltonians whose two-derivative records do not fit one SM: n = 3 at L = J = 6, 2-D at L >= 14) use
+// the product-rule form of the bracket, whose g records hold g[0..J] only (5 instead of 7 units at J = 6): they go to
+// shared memory when they fit (176 KB at n = 3, L = J = 6) with `out` in the CTA's global workspace, else they stay
+// in the workspace and `out` is on chip.  The Y records (warp-uniform loads) are always in the workspace.  All three
+// are reached through generic pointers in these kernels.
 template <bool BIG>
 __device__ __forceinline__ Smem smem_view(const DevPlan& P, const Sched& S, const Ctx& c) {
     Smem v;
     if (BIG) {
-        v.G = c.rec;
-        v.Y = v.G + (P.M + RG_ZERO_RECS) * P.rec_units;
-        v.out = reinterpret_cast<double*>(smem_dyn + RG_RED_UNITS + RG_CTL_UNITS);
+        v.Y = c.rec;
+        if (P.g_smem) {
+            v.G = smem_dyn + RG_RED_UNITS + RG_CTL_UNITS;
+            v.out = c.rec2;
+        } else {
+            v.G = reinterpret_cast<double2*>(c.rec2);
+            v.out = reinterpret_cast<double*>(smem_dyn + RG_RED_UNITS + RG_CTL_UNITS);
+        }
     } else {
         v.G = smem_dyn + RG_RED_UNITS + RG_CTL_UNITS;
         v.Y = v.G + (P.M + RG_ZERO_RECS) * P.rec_units;
@@ -424,6 +438,256 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// BIG kernels: the bracket in product-rule form.  RG.liouville (RG.py:115-117) convolves dA y with Omega_nu g and Omega_nu y with
+// dA g; a lane would have to gather BOTH derivatives of g[nu - nu1] (2J+1 doubles per source mode).  Because
+// Omega.(nu - nu1) = Omega.nu - Omega.nu1 and (a + b) y[a] g[b] = (a y[a]) g[b] + y[a] (b g[b]), the same bracket is
+//
+//     out[nu][j] = (Omega.nu) S1[j] - (j + 1) S2[j],
+//     S1[j] = sum_{nu1} sum_{a+b=j+1, a>=1}  y1[nu1][a-1] g[nu-nu1][b]       y1[a-1] = a y[a]           (= dA y)
+//     S2[j] = sum_{nu1} sum_{a+b=j+1}        y2[nu1][a]   g[nu-nu1][b]       y2[a]   = (Omega.nu1) y[a] (= Omega_nu y)
+//
+// so the gathered record is g itself (J+1 doubles, 6 LDS.128 at J = 10 instead of 11), the y side is what
+// generate_y already produces, and an entry costs 140 DFMAs instead of 130 with 2(J+1) accumulators per lane.
+// (Holds for a generator whose y1 and y2 come from ONE y, as generate_y's do; a caller-supplied pair (y1, y2) --
+// RG.liouville / expm_* through the drop-in API, schedule kind 1 -- takes taylor_general below, which forms
+// Omega_nu g and dA g in registers and multiplies exactly like the reference.)
+//
+// record layouts (doubles):  Y record: [0..J-1] y1 = dA y, [OFF2..OFF2+J] y2 = Omega_nu y, y1[J] (caller-supplied y
+// only) at IDXJ;  G record: g[0..J].  Both padded to an odd number of 16-byte units (conflict-free LDS.128 over a
+// quarter-warp whose record indices are distinct mod 8).
+template <int J>
+struct RecGeomPR {
+    static constexpr int JP = J + 1, OFF2 = J + (J & 1), TOT = OFF2 + JP;
+    static constexpr int ND2 = OFF2 / 2;              // double2 units of the y1 part of a Y record
+    static constexpr int NY2 = (TOT + 1) / 2 - ND2;   // double2 units of the y2 part
+    static constexpr int GU = (JP + 1) / 2;           // double2 units of a G record that hold data
+    static constexpr int IDXJ = (J & 1) ? J : OFF2 + JP;
+    // Every entry runs a branch-free, software-pipelined product on its zero-padded y record (the absent levels are
+    // stored as exact zeros): entries with jm <= LIM_A levels take the product truncated to LIM_A levels of y,
+    // jm <= LIM_B the one truncated to LIM_B, the rest the complete one (J = 10: 3 / 6 / 11 levels, J = 6: 3 / 5 / 7).
+    // rgplan::level_class mirrors this.
+    static constexpr int LIM_A = (J >= 8) ? 3 : (J / 2 > 2 ? J / 2 : 2), LIM_B = (J >= 8) ? 6 : J - 1;
+    // y pairs (double2 units) a product truncated to LIM levels of y reads: y1[i] != 0 iff i + 1 < LIM, y2[a] iff a < LIM
+    __host__ __device__ static constexpr int np1(int LIM) { return LIM / 2 < (J + 1) / 2 ? LIM / 2 : (J + 1) / 2; }
+    __host__ __device__ static constexpr int np2(int LIM) { return (LIM + 1) / 2 < J / 2 + 1 ? (LIM + 1) / 2 : J / 2 + 1; }
+    // double2 unit of the k-th y pair of such a product, in consumption order; past the end: the last pair again
+    __host__ __device__ static constexpr int unit(int LIM, int k) {
+        return k < np1(LIM) ? k : (k < np1(LIM) + np2(LIM) ? ND2 + (k - np1(LIM)) : ND2 + np2(LIM) - 1);
+    }
+};
+
+// Per-lane constants of the gather: biased coords of the lane's output mode, its linear index, limits.
+struct LaneGeoPR {
+    int v0, v1, v2;       // coords + L  (so that v - e, e = biased coord of nu1, is the biased coord of nu - nu1)
+    int lin;              // sum_d v_d * stride_d : centred index of (nu - nu1) = lin - index(nu1)
+    unsigned lim;         // 2L
+    int zero_rec;         // index of the first all-zero record (M)
+    int g_bytes, y_bytes;     // record strides
+    const char* gg;           // the g records: a generic pointer (shared memory when they fit, else the CTA's workspace)
+    const char* gy;           // the Y records: the CTA's global workspace
+};
+
+// next entry: test nu - nu1 against the grid, form the two record addresses.  w = the entry's two list words, read
+// by every lane from the same address two entries ahead (a warp-wide block of words broadcast by SHFL put the
+// shuffle's latency on the critical path of the short, level-truncated products: 6 % of the stall samples).
+// An out-of-range lane gathers the zero record congruent (mod 8) to the record it would have read.
+__device__ __forceinline__ void decode_entry_pr(const LaneGeoPR& q, const uint2& w, uint32_t& gp, uint32_t& yp, int& nat_out) {
+    const uint32_t ec = w.x, ei = w.y;
+    const unsigned u0 = (unsigned)(q.v0 - (int)(ec & 0xff)), u1 = (unsigned)(q.v1 - (int)((ec >> 8) & 0xff)),
+                   u2 = (unsigned)(q.v2 - (int)((ec >> 16) & 0xff));
+    const bool ok = max(max(u0, u1), u2) <= q.lim;
+    const int nat = q.lin - (int)(ei & 0xffff);
+    const int gi = ok ? nat : q.zero_rec + ((nat - q.zero_rec) & (RG_ZERO_RECS - 1));
+    gp = (uint32_t)(gi * q.g_bytes);
+    yp = (uint32_t)((int)(ei >> 16) * q.y_bytes);
+    nat_out = ok ? nat : -1;
+}
+
+__device__ __forceinline__ double2 ldg_pr(const LaneGeoPR& q, uint32_t off) {     // gathered g record: generic
+    double2 v;
+    asm volatile("ld.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(q.gg + off));
+    return v;
+}
+__device__ __forceinline__ double2 ldy_pr(const LaneGeoPR& q, uint32_t off) {     // warp-uniform y pair: global, through L1
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(q.gy + off));
+    return v;
+}
+
+// One list entry of the product-rule bracket, truncated at compile time to LIM levels of y (LIM = J+1: all of them).
+// On entry:  g  = this entry's gathered record, yq = its first y pair.
+// On exit:   gn = the next entry's gathered record (requested right after the decode that sits inside the first rows
+//            of the DFMA stream, so it has the whole product to land), yq = the next entry's first y pair,
+//            (gp, yp) = the next entry's addresses.  The caller alternates (g, gn).
+template <int J, int LIM>
+__device__ __forceinline__ void taylor_leib(double (&S1)[J + 1], double (&S2)[J + 1], const double (&g)[2 * RecGeomPR<J>::GU],
+                                            double (&gn)[2 * RecGeomPR<J>::GU], double2& yq, const LaneGeoPR& q, const uint2& wn,
+                                            uint32_t& gp, uint32_t& yp) {
+    typedef RecGeomPR<J> R;
+    constexpr int N1 = R::np1(LIM), N2 = R::np2(LIM), NP = N1 + N2;
+    uint32_t gp_n = gp, yp_n = yp;
+#pragma unroll
+    for (int k = 0; k < NP; ++k) {
+        const double2 t = yq;
+        if (k == 0) {   // decode the next entry and request its record
+            int nat;
+            decode_entry_pr(q, wn, gp_n, yp_n, nat);
+#pragma unroll
+            for (int u = 0; u < R::GU; ++u) { const double2 v = ldg_pr(q, gp_n + 16 * u); gn[2 * u] = v.x; gn[2 * u + 1] = v.y; }
+        }
+        yq = (k + 1 < NP) ? ldy_pr(q, yp + 16 * R::unit(LIM, k + 1)) : ldy_pr(q, yp_n + 16 * R::unit(LIM, 0));
+        if (k < N1) {
+            // S1[i + b] += y1[i] g[b],  i = a - 1
+            const int i = 2 * k;
+            if (i + 1 < LIM) {
+#pragma unroll
+                for (int b = 0; b <= J - i; ++b) S1[i + b] = fma(t.x, g[b], S1[i + b]);
+            }
+            if (i + 1 < J && i + 2 < LIM) {
+#pragma unroll
+                for (int b = 0; b <= J - i - 1; ++b) S1[i + 1 + b] = fma(t.y, g[b], S1[i + 1 + b]);
+            }
+        } else {
+            // S2[a + b - 1] += y2[a] g[b]
+            const int a = 2 * (k - N1);
+            if (a < LIM) {
+#pragma unroll
+                for (int b = (a == 0 ? 1 : 0); b <= J && a + b - 1 <= J; ++b) S2[a + b - 1] = fma(t.x, g[b], S2[a + b - 1]);
+            }
+            if (a + 1 <= J && a + 1 < LIM) {
+#pragma unroll
+                for (int b = 0; b <= J && a + b <= J; ++b) S2[a + b] = fma(t.y, g[b], S2[a + b]);
+            }
+        }
+    }
+    gp = gp_n; yp = yp_n;
+}
+
+// One list entry of a caller-supplied generator (y1 and y2 are independent arrays: RG.liouville / expm_* through the
+// drop-in API).  acc[j] += sum_{j1+j2=j} y1[j1] (Omega_nu2 g[j2]) - y2[j1] ((j2+1) g[j2+1]) with the two derivatives of
+// g formed in registers, rounded exactly like RG.derivs (RG.py:76).  Not on the fused path; loads on demand.
+template <int J>
+__device__ __forceinline__ void taylor_general(double (&acc)[J + 1], const LaneGeoPR& q, const uint2& w, const double* __restrict__ Omega_nu) {
+    typedef RecGeomPR<J> R;
+    uint32_t gp, yp;
+    int nat;
+    decode_entry_pr(q, w, gp, yp, nat);
+    double g[2 * R::GU];
+#pragma unroll
+    for (int u = 0; u < R::GU; ++u) { const double2 v = ldg_pr(q, gp + 16 * u); g[2 * u] = v.x; g[2 * u + 1] = v.y; }
+    const double om2 = nat >= 0 ? Omega_nu[nat] : 0.0;
+    double gO[J + 1], gD[J + 1];
+#pragma unroll
+    for (int j = 0; j <= J; ++j) { gO[j] = om2 * g[j]; gD[j] = (j < J) ? g[j + 1] * (double)(j + 1) : 0.0; }
+#pragma unroll
+    for (int k = 0; k < R::ND2; ++k) {       // conv(y1, Omega g)
+        const double2 t = ldy_pr(q, yp + 16 * k);
+        const int j1 = 2 * k;
+#pragma unroll
+        for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, gO[j2], acc[j1 + j2]);
+        if (j1 + 1 < J) {
+#pragma unroll
+            for (int j2 = 0; j2 <= J - j1 - 1; ++j2) acc[j1 + 1 + j2] = fma(t.y, gO[j2], acc[j1 + 1 + j2]);
+        }
+    }
+    {   // y1[J] of a caller-supplied generator (zero for generate_y's)
+        double a;
+        asm volatile("ld.global.f64 %0, [%1];" : "=d"(a) : "l"(q.gy + yp + 8 * R::IDXJ));
+        acc[J] = fma(a, gO[0], acc[J]);
+    }
+#pragma unroll
+    for (int k = 0; k < R::NY2; ++k) {       // - conv(y2, dA g)
+        const double2 t = ldy_pr(q, yp + 16 * (R::ND2 + k));
+        const int j1 = 2 * k;
+        if (j1 <= J) {
+#pragma unroll
+            for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, gD[j2], acc[j1 + j2]);
+        }
+        if (j1 + 1 <= J) {
+#pragma unroll
+            for (int j2 = 0; j2 < J && j1 + 1 + j2 <= J; ++j2) acc[j1 + 1 + j2] = fma(-t.y, gD[j2], acc[j1 + 1 + j2]);
+        }
+    }
+}
+
+__device__ __forceinline__ LaneGeoPR lane_geometry_pr(const Ctx& c, int box) {
+    const DevPlan& P = RG_PLAN(c);
+    const Sched& S = RG_SCHED(c);
+    const Smem sm = smem_view<true>(P, S, c);
+    const int lane = threadIdx.x & 31;
+    const uint32_t mc = S.lane_coord[box * 32 + lane];
+    LaneGeoPR q;
+    q.v0 = (int)(mc & 0xff) + P.L; q.v1 = (int)((mc >> 8) & 0xff) + P.L; q.v2 = (int)((mc >> 16) & 0xff) + P.L;
+    q.lin = q.v0 * P.stride0 + q.v1 * P.stride1 + q.v2 * P.stride2;
+    q.lim = 2u * (unsigned)P.L;
+    q.zero_rec = P.M;
+    q.g_bytes = P.g_units * 16;
+    q.y_bytes = P.rec_units * 16;
+    q.gg = reinterpret_cast<const char*>(sm.G);
+    q.gy = reinterpret_cast<const char*>(sm.Y);
+    return q;
+}
+
+// One piece of a box's source list on the fused path: S1, S2 of the product-rule form, summed from zero.  The
+// planner sorts a list by level class, so a piece is at most three runs (ends e_full <= e_mid <= e_end): one tight
+// loop per class, two entries per trip so that the gathered record alternates between two register sets.
+template <int J>
+__device__ __forceinline__ void conv_piece_pr(const Ctx& c, int box, int e_begin, int e_full, int e_mid, int e_end,
+                                           double (&S1)[J + 1], double (&S2)[J + 1]) {
+    typedef RecGeomPR<J> R;
+    const uint2* const entries = RG_SCHED(c).entries;
+    const LaneGeoPR q = lane_geometry_pr(c, box);
+#pragma unroll
+    for (int j = 0; j <= J; ++j) { S1[j] = 0.0; S2[j] = 0.0; }
+    if (e_begin >= e_end) return;
+    double ga[2 * R::GU], gb[2 * R::GU];
+    double2 yq;
+    uint32_t gp, yp;
+    {
+        int nat;
+        decode_entry_pr(q, entries[e_begin], gp, yp, nat);
+    }
+#pragma unroll
+    for (int u = 0; u < R::GU; ++u) { const double2 v = ldg_pr(q, gp + 16 * u); ga[2 * u] = v.x; ga[2 * u + 1] = v.y; }
+    yq = ldy_pr(q, yp);
+    // list words of the next entry (decoded inside the current product) and of the one after (in flight); past the
+    // end the last entry is read again (harmless, keeps the loop uniform)
+    const int last = e_end - 1;
+    int i = e_begin;
+    uint2 wn = entries[min(i + 1, last)];
+#define RG_RUN(LIM, RUN_END)                                                                      \
+    _Pragma("unroll 1")                                                                           \
+    for (; i + 2 <= (RUN_END); i += 2) {                                                          \
+        const uint2 w2 = entries[min(i + 2, last)], w3 = entries[min(i + 3, last)];               \
+        taylor_leib<J, LIM>(S1, S2, ga, gb, yq, q, wn, gp, yp);                              \
+        taylor_leib<J, LIM>(S1, S2, gb, ga, yq, q, w2, gp, yp);                              \
+        wn = w3;                                                                                  \
+    }                                                                                             \
+    if (i < (RUN_END)) {                                                                          \
+        const uint2 w2 = entries[min(i + 2, last)];                                               \
+        taylor_leib<J, LIM>(S1, S2, ga, gb, yq, q, wn, gp, yp);                              \
+        _Pragma("unroll")                                                                         \
+        for (int u = 0; u < 2 * R::GU; ++u) ga[u] = gb[u];                                        \
+        wn = w2; ++i;                                                                             \
+    }
+    RG_RUN(J + 1, e_full)
+    RG_RUN(R::LIM_B, e_mid)
+    RG_RUN(R::LIM_A, e_end)
+#undef RG_RUN
+}
+
+// One piece of a caller-supplied generator's list (schedule kind 1): the bracket itself in acc.
+template <int J>
+__device__ __noinline__ void conv_piece_general(const Ctx& c, int box, int e_begin, int e_end, double (&acc)[J + 1]) {
+    const uint2* const entries = RG_SCHED(c).entries;
+    const LaneGeoPR q = lane_geometry_pr(c, box);
+#pragma unroll
+    for (int j = 0; j <= J; ++j) acc[j] = 0.0;
+#pragma unroll 1
+    for (int i = e_begin; i < e_end; ++i) taylor_general<J>(acc, q, entries[i], c.Omega_nu);
+}
+
 // out[nu][j] = conv(dA y, Omega g) - conv(Omega y, dA g)  (G, Y in shared memory).  Ends with a barrier.
 // Every warp owns up to S.maxp pieces of the boxes' source lists per stage: heads (rank 0) store their sums,
 // the single continuation a warp may hold (rank r > 0) adds once the box's counter says r, stage-1 pieces once
@@ -471,7 +735,23 @@ __device__ RG_CONV_ATTR void conv_all(Ctx& c) {
             for (int q = 0; q < S.maxp; ++q) {
                 const int4 p = pieces[pw * S.maxp + q];      // heads first, the continuation (if any) last
                 if (p.x < 0) continue;
-                conv_piece<J, BIG>(c, p.x, p.y, p.z, acc);
+                if constexpr (BIG) {
+                    // product-rule form: the piece's contribution is (Omega.nu) S1 - (j+1) S2 of its own partial sums
+                    // (the map is linear, so pieces add); a caller-supplied generator takes the general product
+                    if (S.general) {
+                        conv_piece_general<J>(c, p.x, p.y, p.z, acc);
+                    } else {
+                        double S1[JP], S2[JP];
+                        const int2 r = S.piece_runs[((size_t)st * S.n_warps + pw) * S.maxp + q];
+                        conv_piece_pr<J>(c, p.x, p.y, r.x, r.y, p.z, S1, S2);
+                        const int nu_ = S.lane_out[p.x * 32 + lane];
+                        const double om = nu_ >= 0 ? c.Omega_nu[nu_] : 0.0;
+#pragma unroll
+                        for (int j = 0; j < JP; ++j) acc[j] = om * S1[j] - (double)(j + 1) * S2[j];
+                    }
+                } else {
+                    conv_piece<J, false>(c, p.x, p.y, p.z, acc);
+                }
                 if (lane == 0) {
                     if (st) while (vctl[nb_all] < need0) {}
                     while (vctl[p.x] != p.w) {}
@@ -510,7 +790,9 @@ __device__ RG_CONV_ATTR void conv_all(Ctx& c) {
             for (int j = 0; j < JP; ++j) v[j] = out[nu * JP + j];
             for (int r = 0; r < c.csize; ++r) {
                 if (r == c.crank) continue;
-                double* o = cl.map_shared_rank(out, r) + nu * JP;
+                // peers are consecutive CTAs: their `out` is at the same shared-memory offset (DSMEM), or -- BIG kernels
+                // with the g records on chip -- in their slice of the global workspace
+                double* o = ((BIG && RG_PLAN(c).g_smem) ? out + (long long)(r - c.crank) * RG_PLAN(c).ws_stride : cl.map_shared_rank(out, r)) + nu * JP;
 #pragma unroll
                 for (int j = 0; j < JP; ++j) o[j] = v[j];
             }
@@ -536,23 +818,34 @@ __device__ __noinline__ void build_G(const Ctx& c, const double* __restrict__ sr
     const bool mirror = c.symm != 0;
     const int nmax = mirror ? (M + 1) / 2 : M;
     for (int nu = threadIdx.x; nu < nmax; nu += blockDim.x) {
-        double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
-        const double om = c.Omega_nu[nu];
         const int mu = M - 1 - nu;
         double g[J + 1];
 #pragma unroll
         for (int j = 0; j <= J; ++j) g[j] = src[j * M + nu];
+        if constexpr (BIG) {   // product-rule form: the record is g itself (and so is the mirror's: g is symmetric)
+            double* r = reinterpret_cast<double*>(sm.G + nu * P.g_units);
 #pragma unroll
-        for (int j = 0; j <= J; ++j) {
-            r[P.off2 + j] = om * g[j];
-            if (j < J) r[j] = g[j + 1] * (double)(j + 1);
-        }
-        if (mirror && mu != nu) {
-            double* r2 = reinterpret_cast<double*>(sm.G + mu * P.rec_units);
+            for (int j = 0; j <= J; ++j) r[j] = g[j];
+            if (mirror && mu != nu) {
+                double* r2 = reinterpret_cast<double*>(sm.G + mu * P.g_units);
+#pragma unroll
+                for (int j = 0; j <= J; ++j) r2[j] = g[j];
+            }
+        } else {
+            double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
+            const double om = c.Omega_nu[nu];
 #pragma unroll
             for (int j = 0; j <= J; ++j) {
-                r2[P.off2 + j] = -(om * g[j]);
-                if (j < J) r2[j] = g[j + 1] * (double)(j + 1);
+                r[P.off2 + j] = om * g[j];
+                if (j < J) r[j] = g[j + 1] * (double)(j + 1);
+            }
+            if (mirror && mu != nu) {
+                double* r2 = reinterpret_cast<double*>(sm.G + mu * P.rec_units);
+#pragma unroll
+                for (int j = 0; j <= J; ++j) {
+                    r2[P.off2 + j] = -(om * g[j]);
+                    if (j < J) r2[j] = g[j + 1] * (double)(j + 1);
+                }
             }
         }
     }
@@ -624,8 +917,14 @@ __device__ RG_EPI_ATTR double2 series_epilogue_impl(Ctx& c, double* __restrict__
             if (nua >= nmax) { nua -= nmax; ++ja; }
             v_[q] = 0.0; fo_[q] = 0.0;
             if (i < total) {
-                const double* r = reinterpret_cast<const double*>(sm.G + nu * P.rec_units);
-                const double dg = (j < J) ? r[j] : 0.0;
+                double dg;      // dA g  (RG.py:76)
+                if constexpr (BIG) {
+                    const double* r = reinterpret_cast<const double*>(sm.G + nu * P.g_units);
+                    dg = (j < J) ? r[j + 1] * (double)(j + 1) : 0.0;
+                } else {
+                    const double* r = reinterpret_cast<const double*>(sm.G + nu * P.rec_units);
+                    dg = (j < J) ? r[j] : 0.0;
+                }
                 double v = a0 * dg + sm.out[nu * JP + j];
                 if (first) {
                     double t = y3[j * M + nu];
@@ -651,19 +950,28 @@ __device__ RG_EPI_ATTR double2 series_epilogue_impl(Ctx& c, double* __restrict__
                 const double om = c.Omega_nu[nu];
                 const double w = (!SUM && type == 3) ? P.normw[nu] : 1.0;
                 const double v = v_[q], fn = fo_[q] + v;
-                double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
                 f[j * M + nu] = fn;
                 norm_acc(type, ps, v, w);
                 norm_acc(type, pf, fn, w);
-                r[P.off2 + j] = om * v;
-                if (j > 0) r[j - 1] = v * (double)j;
                 if (twin) {
-                    double* r2 = reinterpret_cast<double*>(sm.G + mu * P.rec_units);
                     f[j * M + mu] = fn;
                     norm_acc(type, ps, v, w);
                     norm_acc(type, pf, fn, w);
-                    r2[P.off2 + j] = -(om * v);
-                    if (j > 0) r2[j - 1] = v * (double)j;
+                }
+                if constexpr (BIG) {
+                    // item (j, nu) read the OLD g[j+1] above and writes the new g[j]: (j+1, nu), which overwrites g[j+1],
+                    // is in the same or a later chunk (behind this chunk's barrier)
+                    reinterpret_cast<double*>(sm.G + nu * P.g_units)[j] = v;
+                    if (twin) reinterpret_cast<double*>(sm.G + mu * P.g_units)[j] = v;
+                } else {
+                    double* r = reinterpret_cast<double*>(sm.G + nu * P.rec_units);
+                    r[P.off2 + j] = om * v;
+                    if (j > 0) r[j - 1] = v * (double)j;
+                    if (twin) {
+                        double* r2 = reinterpret_cast<double*>(sm.G + mu * P.rec_units);
+                        r2[P.off2 + j] = -(om * v);
+                        if (j > 0) r2[j - 1] = v * (double)j;
+                    }
                 }
             }
         }
@@ -889,18 +1197,9 @@ __device__ __noinline__ double* rg_map_dev(Ctx& c, double* f, const Tables& T, i
     double* fa = c.ws + (size_t)WS_FA * P.vecjl;
     double* fb = c.ws + (size_t)WS_FB * P.vecjl;
     c.Omega_nu = T.Omega_nu + (size_t)(k + 1) * P.M;
-    if (c.fa != fa) {
-        // f lives in shared memory: re-index through the global scratch and bring the result home (one extra pass
-        // per rg_map, against ~90 Lie steps whose every term reads and writes f)
-        reindex_rescale<J>(c, f, fb, T.nrm[k]);
-        copy_arr(c, c.fa, fb);
-        __syncthreads();
-        f = c.fa;
-    } else {
-        double* dst = (f == fa) ? fb : fa;
-        reindex_rescale<J>(c, f, dst, T.nrm[k]);
-        f = dst;
-    }
+    double* dst = (f == fa) ? fb : fa;
+    reindex_rescale<J>(c, f, dst, T.nrm[k]);
+    f = dst;
     int err = 0, kl = 0;
     double2 nn = sym_and_norms<J>(c, f, false);
     while (P.tol_max > nn.x && nn.x > P.tol_min && kl < P.max_lie && c.n_liou - c.budget_base <= P.max_liouville) {

@@ -65,16 +65,19 @@ __global__ void __launch_bounds__((J >= 8 || BIG) ? 384 : 256, (J >= 8 || BIG) ?
     int* sh_item = reinterpret_cast<int*>(smem_red() + 64);
     c.ws = job.ws_base + (size_t)blockIdx.x * (size_t)P.ws_stride;
     c.rec = reinterpret_cast<double2*>(c.ws + (size_t)P.rec_offset);
+    c.rec2 = c.ws + (size_t)P.rec2_offset;
     const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
     c.Omega_nu = T.Omega_nu;
-    // zero all records once (pads and the all-zero record stay zero for the life of the CTA)
-    {
-        const int nd2 = (P.M + RG_ZERO_RECS + (BIG ? P.M : RG_SCHED(c).n_support)) * P.rec_units;
+    // zero all records once (pads and the all-zero records stay zero for the life of the CTA)
+    if (BIG) {
+        const int ng = (P.M + RG_ZERO_RECS) * P.g_units, ny = P.M * P.rec_units;
+        for (int i = threadIdx.x; i < ng; i += blockDim.x) sm.G[i] = make_double2(0.0, 0.0);
+        for (int i = threadIdx.x; i < ny; i += blockDim.x) sm.Y[i] = make_double2(0.0, 0.0);
+    } else {
+        const int nd2 = (P.M + RG_ZERO_RECS + RG_SCHED(c).n_support) * P.rec_units;
         for (int i = threadIdx.x; i < nd2; i += blockDim.x) sm.G[i] = make_double2(0.0, 0.0);
     }
-    // the coefficient array: in shared memory behind `out` when the plan says it fits for this schedule kind
-    double* fa = ((P.f_smem >> job.sched) & 1) ? sm.out + (size_t)P.M * P.JP : c.ws + (size_t)WS_FA * P.vecjl;
-    c.fa = fa;
+    double* fa = c.ws + (size_t)WS_FA * P.vecjl;
     const int M = P.M, c0 = (M - 1) / 2;
     for (;;) {
         if (c.csize > 1) {

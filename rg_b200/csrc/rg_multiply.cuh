@@ -22,10 +22,10 @@ __device__ __noinline__ void liouville_apply(Ctx& c, const double* src, double* 
     __syncthreads();
     conv_all<J, BIG>(c);
     for (int nu = threadIdx.x; nu < M; nu += blockDim.x) {
-        const double* r = reinterpret_cast<const double*>(sm.G + nu * P.rec_units);
+        const double* r = reinterpret_cast<const double*>(sm.G + nu * (BIG ? P.g_units : P.rec_units));
 #pragma unroll
         for (int j = 0; j < JP; ++j) {
-            const double dg = (j < J) ? r[j] : 0.0;
+            const double dg = (j < J) ? (BIG ? r[j + 1] * (double)(j + 1) : r[j]) : 0.0;   // dA src  (RG.py:76)
             const double v = a0 * dg + sm.out[nu * JP + j];
             dst[j * M + nu] = negate ? -v : v;
         }

@@ -22,6 +22,7 @@ struct Geometry {
     int dim = 0, L = 0, J = 0, JP = 0, n1 = 0, M = 0, vecjl = 0;
     int off2 = 0;       // record layout: [0..J-1] d-type (dA g or dA y), [off2..off2+J] Omega-type
     int rec_units = 0;  // 16-byte units per record (odd => conflict-free LDS.128 over consecutive modes)
+    int g_units = 0;    // 16-byte units of a g-only record (g[0..J], product-rule form of the BIG kernels); odd too
     int stride[4] = {0, 0, 0, 0};
     void init(int dim_, int L_, int J_) {
         dim = dim_; L = L_; J = J_; JP = J + 1; n1 = 2 * L + 1;
@@ -31,6 +32,8 @@ struct Geometry {
         int tot = off2 + JP;
         rec_units = (tot + 1) / 2;
         if ((rec_units & 1) == 0) rec_units += 1;
+        g_units = (JP + 1) / 2;
+        if ((g_units & 1) == 0) g_units += 1;
         int s = 1;
         for (int d = dim - 1; d >= 0; --d) { stride[d] = s; s *= n1; }
         for (int d = dim; d < 4; ++d) stride[d] = 0;
@@ -58,6 +61,15 @@ inline int taylor_fma(int jm, int J) {
     int c = 0;
     for (int j1 = 0; j1 < J; ++j1) if (j1 + 1 < jm) c += J - j1 + 1;
     for (int j1 = 0; j1 <= J; ++j1) if (j1 < jm) c += std::min(J, J - j1 + 1);
+    return c;
+}
+
+// FMAs the device ISSUES for such a pair in the product-rule form of the bracket (BIG kernels; rg_device.cuh, taylor_leib):
+//   S1: y1[i] g[b], i + 1 < jm, b <= J - i;   S2: y2[a] g[b], a < jm, a + b - 1 in [0, J]      (140 instead of 130 at J = 10)
+inline int taylor_fma_issued_pr(int jm, int J) {
+    int c = 0;
+    for (int i = 0; i < J; ++i) if (i + 1 < jm) c += J - i + 1;
+    for (int a = 0; a <= J; ++a) if (a < jm) c += (a == 0) ? J : J + 2 - a;
     return c;
 }
 
@@ -95,6 +107,9 @@ struct Schedule {
     std::vector<int32_t> lane_out;     // [NB*32] centred mode index or -1
     std::vector<uint32_t> lane_coord;  // [NB*32] packed biased coords (idle lanes: first coordinate 255)
     std::vector<Piece> pieces;         // [n_stages][NW*maxp], box = -1 for unused slots; heads first, continuation last
+    std::vector<int32_t> piece_runs;   // [n_stages][NW*maxp][2]: end of the piece's run of complete products, end of its LIM_B run
+    bool general = false;              // caller-supplied generator (dense): every entry takes the general product
+    bool prule = false;                // costs counted for the product-rule form of the bracket (BIG kernels)
     std::vector<uint32_t> entries;     // [n*2]: {biased coords of nu1 (8 bits each) | jm<<24, centred index | rec<<16}
     std::vector<int32_t> supp_rec;     // [M] record index of centred nu1, -1 if not in support
     std::vector<uint8_t> jm;           // [M] 1 + highest I^- level (0 = not in support)
@@ -107,11 +122,13 @@ struct Schedule {
 // that the y1[J] term of a caller-supplied generator is kept).  half: only modes c <= centre are computed.
 // n_warps: warps of the whole cluster (csize CTAs x warps per CTA).
 inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t>& mask, bool dense, bool half, int n_warps, int csize,
-                                   bool allow_two_stage) {
+                                   bool allow_two_stage, bool prule) {
     Schedule s;
     const int M = g.M, L = g.L, J = g.J, c0 = (M - 1) / 2;
     s.half = half;
     s.csize = csize;
+    s.general = dense;
+    s.prule = prule;
     s.jm.assign(M, 0);
     s.supp_rec.assign(M, -1);
     for (int c = 0; c < M; ++c) {
@@ -122,7 +139,10 @@ inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t
         if (jm > 0) s.supp_rec[c] = s.n_support++;
     }
     auto tcost = [&](int c1) { return (int64_t)taylor_fma(std::min<int>(s.jm[c1], g.JP), J) + (s.jm[c1] > g.JP ? 1 : 0); };
-    auto tissued = [&](int c1) { return s.jm[c1] > g.JP ? tcost(c1) : (int64_t)taylor_fma(level_class(s.jm[c1], J), J); };
+    auto tissued = [&](int c1) {
+        if (s.jm[c1] > g.JP) return tcost(c1);
+        return (int64_t)(prule ? taylor_fma_issued_pr(level_class(s.jm[c1], J), J) : taylor_fma(level_class(s.jm[c1], J), J));
+    };
     // issue-slot model of one list entry, used to balance the warps: a DFMA holds the issue port ~2.65 cycles on
     // average (operand-reuse misses included), every entry carries ~67 other instructions (loads, decode, loop)
     auto wcost_of = [&](int c1) { return (int64_t)(2.65 * (double)tissued(c1)) + 67; };
@@ -366,15 +386,30 @@ inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t
         }
     }
     for (int i = 0; i < NW; ++i) { s.cost_max = std::max(s.cost_max, wcost[i]); }
+    // run ends of every piece: its list is sorted by level class (complete products, LIM_B, LIM_A)
+    s.piece_runs.assign(s.pieces.size() * 2, 0);
+    for (size_t i = 0; i < s.pieces.size(); ++i) {
+        const Piece& pc = s.pieces[i];
+        if (pc.box < 0) continue;
+        int e_full = pc.begin, e_mid;
+        auto cls = [&](int e) { return level_class((int)(s.entries[2 * (size_t)e] >> 24), J); };
+        const int lim_a = (J >= 8) ? 3 : (J / 2 > 2 ? J / 2 : 2), lim_b = (J >= 8) ? 6 : J - 1;   // as in level_class
+        while (e_full < pc.end && cls(e_full) > std::max(lim_a, lim_b)) ++e_full;    // complete products (and the general ones)
+        e_mid = e_full;
+        if (lim_b > lim_a) while (e_mid < pc.end && cls(e_mid) == lim_b) ++e_mid;
+        for (int e = e_mid; e < pc.end; ++e) if (cls(e) > lim_a) { s.n_warps = -1; return s; }    // list not sorted: cannot happen
+        s.piece_runs[2 * i] = e_full; s.piece_runs[2 * i + 1] = e_mid;
+    }
     return s;
 }
 
 // In three dimensions the two-partition schedule is not always the better one (the 8 x 4 x 1 blocks fit a grid of
 // 13^3 modes, not one of 9^3): build both and keep the one that issues fewer FMAs.
-inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& mask, bool dense, bool half, int n_warps, int csize = 1) {
-    Schedule two = make_schedule_impl(g, mask, dense, half, n_warps, csize, true);
+inline Schedule make_schedule(const Geometry& g, const std::vector<uint16_t>& mask, bool dense, bool half, int n_warps, int csize = 1,
+                              bool prule = false) {
+    Schedule two = make_schedule_impl(g, mask, dense, half, n_warps, csize, true, prule);
     if (g.dim < 3 || two.n_stages < 2) return two;
-    Schedule one = make_schedule_impl(g, mask, dense, half, n_warps, csize, false);
+    Schedule one = make_schedule_impl(g, mask, dense, half, n_warps, csize, false, prule);
     if (two.n_warps < 0) return one;
     if (one.n_warps < 0) return two;
     return one.fma_executed <= two.fma_executed ? one : two;

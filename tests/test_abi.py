@@ -261,7 +261,7 @@ def test_schedule_geometry_config5():
                 have |= set((s["entries"][b:e, 1] & 0xffff).astype(int))
             assert have == set(supp[need & mine]), box
         cost[mode] = s["cost"]
-        assert s["cost"][0] / s["cost"][1] > 0.62, "two partitions + level classes keep more than 62% of the issued lane-FMAs useful"
+        assert s["cost"][0] / s["cost"][1] > 0.57, "two partitions + level classes: useful/issued = lane efficiency (0.65) x 54/60 (this size runs the BIG kernel: product-rule form, 60 DFMAs per complete pair at J = 6 for 54 algorithmic ones)"
     assert abs(cost[2][0] / cost[0][0] - 0.5) < 0.01
 
 
