@@ -475,6 +475,12 @@ struct RecGeomPR {
     __host__ __device__ static constexpr int unit(int LIM, int k) {
         return k < np1(LIM) ? k : (k < np1(LIM) + np2(LIM) ? ND2 + (k - np1(LIM)) : ND2 + np2(LIM) - 1);
     }
+    // The y pairs come from the CTA's global workspace (through L1, L2 behind it).  Up to J = 8 the registers allow
+    // ALL pairs of the NEXT entry to be requested at the top of the current one (a whole product of latency cover:
+    // ncu showed 4.7 long-scoreboard stalls per issue with a window of one pair); beyond that a rolling window of one.
+    static constexpr int N1MAX = (J + 1) / 2, N2MAX = J / 2 + 1, NPMAX = N1MAX + N2MAX;
+    static constexpr bool YALL = (J <= 8);
+    static constexpr int YREGS = YALL ? NPMAX : 1;
 };
 
 // Per-lane constants of the gather: biased coords of the lane's output mode, its linear index, limits.
@@ -522,21 +528,30 @@ __device__ __forceinline__ double2 ldy_pr(const LaneGeoPR& q, uint32_t off) {   
 //            (gp, yp) = the next entry's addresses.  The caller alternates (g, gn).
 template <int J, int LIM>
 __device__ __forceinline__ void taylor_leib(double (&S1)[J + 1], double (&S2)[J + 1], const double (&g)[2 * RecGeomPR<J>::GU],
-                                            double (&gn)[2 * RecGeomPR<J>::GU], double2& yq, const LaneGeoPR& q, const uint2& wn,
+                                            double (&gn)[2 * RecGeomPR<J>::GU], double2 (&y)[RecGeomPR<J>::YREGS],
+                                            double2 (&yn)[RecGeomPR<J>::YREGS], const LaneGeoPR& q, const uint2& wn,
                                             uint32_t& gp, uint32_t& yp) {
     typedef RecGeomPR<J> R;
     constexpr int N1 = R::np1(LIM), N2 = R::np2(LIM), NP = N1 + N2;
     uint32_t gp_n = gp, yp_n = yp;
 #pragma unroll
     for (int k = 0; k < NP; ++k) {
-        const double2 t = yq;
-        if (k == 0) {   // decode the next entry and request its record
+        // YALL: pair slots are fixed whatever the class -- y1 pair p in slot p, y2 pair p in slot N1MAX + p -- because the
+        // next entry (requested with THIS entry's class, a superset) may run a lower one
+        const double2 t = R::YALL ? y[k < N1 ? k : R::N1MAX + (k - N1)] : y[0];
+        if (k == 0) {   // decode the next entry and request its record (and, registers permitting, all its y pairs)
             int nat;
             decode_entry_pr(q, wn, gp_n, yp_n, nat);
 #pragma unroll
             for (int u = 0; u < R::GU; ++u) { const double2 v = ldg_pr(q, gp_n + 16 * u); gn[2 * u] = v.x; gn[2 * u + 1] = v.y; }
+            if (R::YALL) {
+#pragma unroll
+                for (int kk = 0; kk < N1; ++kk) yn[kk] = ldy_pr(q, yp_n + 16 * kk);
+#pragma unroll
+                for (int kk = 0; kk < N2; ++kk) yn[R::N1MAX + kk] = ldy_pr(q, yp_n + 16 * (R::ND2 + kk));
+            }
         }
-        yq = (k + 1 < NP) ? ldy_pr(q, yp + 16 * R::unit(LIM, k + 1)) : ldy_pr(q, yp_n + 16 * R::unit(LIM, 0));
+        if (!R::YALL) y[0] = (k + 1 < NP) ? ldy_pr(q, yp + 16 * R::unit(LIM, k + 1)) : ldy_pr(q, yp_n + 16 * R::unit(LIM, 0));
         if (k < N1) {
             // S1[i + b] += y1[i] g[b],  i = a - 1
             const int i = 2 * k;
@@ -642,7 +657,7 @@ __device__ __forceinline__ void conv_piece_pr(const Ctx& c, int box, int e_begin
     for (int j = 0; j <= J; ++j) { S1[j] = 0.0; S2[j] = 0.0; }
     if (e_begin >= e_end) return;
     double ga[2 * R::GU], gb[2 * R::GU];
-    double2 yq;
+    double2 ya[R::YREGS], yb[R::YREGS];
     uint32_t gp, yp;
     {
         int nat;
@@ -650,7 +665,14 @@ __device__ __forceinline__ void conv_piece_pr(const Ctx& c, int box, int e_begin
     }
 #pragma unroll
     for (int u = 0; u < R::GU; ++u) { const double2 v = ldg_pr(q, gp + 16 * u); ga[2 * u] = v.x; ga[2 * u + 1] = v.y; }
-    yq = ldy_pr(q, yp);
+    if (R::YALL) {
+#pragma unroll
+        for (int k = 0; k < R::N1MAX; ++k) ya[k] = ldy_pr(q, yp + 16 * k);
+#pragma unroll
+        for (int k = 0; k < R::N2MAX; ++k) ya[R::N1MAX + k] = ldy_pr(q, yp + 16 * (R::ND2 + k));
+    } else {
+        ya[0] = ldy_pr(q, yp);
+    }
     // list words of the next entry (decoded inside the current product) and of the one after (in flight); past the
     // end the last entry is read again (harmless, keeps the loop uniform)
     const int last = e_end - 1;
@@ -660,15 +682,20 @@ __device__ __forceinline__ void conv_piece_pr(const Ctx& c, int box, int e_begin
     _Pragma("unroll 1")                                                                           \
     for (; i + 2 <= (RUN_END); i += 2) {                                                          \
         const uint2 w2 = entries[min(i + 2, last)], w3 = entries[min(i + 3, last)];               \
-        taylor_leib<J, LIM>(S1, S2, ga, gb, yq, q, wn, gp, yp);                              \
-        taylor_leib<J, LIM>(S1, S2, gb, ga, yq, q, w2, gp, yp);                              \
+        taylor_leib<J, LIM>(S1, S2, ga, gb, ya, yb, q, wn, gp, yp);                               \
+        if (R::YALL) taylor_leib<J, LIM>(S1, S2, gb, ga, yb, ya, q, w2, gp, yp);                  \
+        else taylor_leib<J, LIM>(S1, S2, gb, ga, ya, yb, q, w2, gp, yp);                          \
         wn = w3;                                                                                  \
     }                                                                                             \
     if (i < (RUN_END)) {                                                                          \
         const uint2 w2 = entries[min(i + 2, last)];                                               \
-        taylor_leib<J, LIM>(S1, S2, ga, gb, yq, q, wn, gp, yp);                              \
+        taylor_leib<J, LIM>(S1, S2, ga, gb, ya, yb, q, wn, gp, yp);                               \
         _Pragma("unroll")                                                                         \
         for (int u = 0; u < 2 * R::GU; ++u) ga[u] = gb[u];                                        \
+        if (R::YALL) {                                                                            \
+            _Pragma("unroll")                                                                     \
+            for (int u = 0; u < R::YREGS; ++u) ya[u] = yb[u];                                     \
+        }                                                                                         \
         wn = w2; ++i;                                                                             \
     }
     RG_RUN(J + 1, e_full)

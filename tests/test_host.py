@@ -120,6 +120,11 @@ assert np.array_equal(got, full), (rank, got[:5])
 f64 = np.linspace(0, 1, 2 * n).reshape(n, 2)
 got = rg_modules.gather_sharded(f64[idx].copy().view(np.int64), n, rank, world).view(np.float64)
 assert np.array_equal(got, f64)
+# a shard may be empty (fewer items than ranks: compute_surface with Nxy < world size)
+one = np.array([[7, 8]], dtype=np.int64)
+idx1 = rg_modules.shard_indices(1, rank, world)
+got = rg_modules.gather_sharded(one[idx1].reshape(len(idx1), 2), 1, rank, world)
+assert np.array_equal(got, one), (rank, got)
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
@@ -136,3 +141,15 @@ def test_gather_world_size_2_gloo(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=300)
         assert p.returncode == 0, out.decode()[-2000:]
+
+
+def test_bench_reference_sample_is_the_prescribed_subsample():
+    """bench.py's CPU arm runs the 16x16 strided subsample BASELINE.md 3.2 prescribes (ix, iy in {8, 24, ..., 248}) in stock
+    order (y outer, x inner, RG_modules.py:138-139) -- the points of golden G-C."""
+    sys.path.insert(0, ROOT)
+    import bench
+    pts, flat, desc = bench.sub16_points(256)
+    g = golden("region_L10J10_sub16_expm_onestep")
+    assert len(pts) == 256 and flat[0] == 8 * 256 + 8 and flat[-1] == 248 * 256 + 248
+    assert np.allclose([p[0] for p in pts[:16]], g["xs"]) and np.allclose([p[1] for p in pts[::16]], g["ys"])
+    assert bench.reference_dir() is None or os.path.isfile(os.path.join(bench.reference_dir(), "RG_modules.py"))
