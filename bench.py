@@ -354,7 +354,9 @@ def main_b200(a):
         peak = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak_r01.json")))["dfma_tflops"]
         ach = 2.0 * useful / dev_sum * 1e-12            # this rank's kernel, this rank's time
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "ncu_bench_traffic_r01.json")
+        tpath = os.path.join(ROOT, "profiles", "ncu_bench_traffic_r02.json")
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "ncu_bench_traffic_r01.json")
         if world == 1 and a.nxy == GRID["Nxy"] and a.ct == "expm_onestep" and os.path.exists(tpath):
             tj = json.load(open(tpath))                 # ncu capture of this very launch (one launch per step)
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
@@ -373,8 +375,8 @@ def main_b200(a):
                     "h2d_bytes_per_step": int(h_amps.numel() * 8), "d2h_bytes_per_step": int(3 * n_loc * 4)},
             "gpu_launches": a.steps * world,
             "roofline": {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, profiles/ncu_bench_traffic_r01.json; "
-                                                             "compute-bound kernel: 0.08 % of the HBM peak, L2 write-back of the workspace)",
+                         "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, %s; compute-bound kernel: "
+                                                             "< 0.1 %% of the HBM peak, L2 write-back of the workspace)" % os.path.relpath(tpath, ROOT),
                          "kernel": "rg_kernel<10, false> (fused converge: conv_all + series epilogue)",
                          "peak_source": "measured DFMA peak, tools/fp64_peak.cu on this pool (profiles/fp64_peak_r01.json)",
                          "liouville_evaluations": int(liou_all),
