@@ -174,7 +174,7 @@ __device__ __forceinline__ double2 block_reduce2(double* red, int type, double a
 }
 
 // ------------------------------------------------------------------------------------------------
-// Taylor product of one (nu1, nu2) pair: acc[j] += sum_{j1+j2=j} dAy[j1]*Omg[j2] - Omy[j1]*dAg[j2]
+// Shared-memory kernels (BIG = false).  Taylor product of one (nu1, nu2) pair: acc[j] += sum_{j1+j2=j} dAy[j1]*Omg[j2] - Omy[j1]*dAg[j2]
 // record layout (doubles): [0..J-1] d-type, [OFF2..OFF2+J] Omega-type, y1[J] (caller-supplied y only) at IDXJ.
 //
 // Everything the inner loop reads from shared memory is in flight long before it is consumed:
@@ -229,9 +229,8 @@ struct LaneGeo {
     int lin;              // sum_d v_d * stride_d : centred index of (nu - nu1) = lin - index(nu1)
     unsigned lim;         // 2L
     int zero_rec;         // index of the first all-zero record (M)
-    uint32_t g_base, y_base;  // shared-memory byte addresses of G and Y (BIG: byte offsets from gb)
+    uint32_t g_base, y_base;  // shared-memory byte addresses of G and Y
     int rec_bytes;
-    const char* gb;           // BIG: the CTA's global record block
 };
 
 // next entry: test nu - nu1 against the grid, form the two record addresses.  w = the entry's two list words, read
@@ -249,11 +248,9 @@ __device__ __forceinline__ void decode_entry(const LaneGeo& q, const uint2& w, u
     yp = q.y_base + (uint32_t)((int)(ei >> 16) * q.rec_bytes);
 }
 
-template <bool BIG>
 __device__ __forceinline__ double2 ldrec(const LaneGeo& q, uint32_t addr) {
     double2 v;
-    if (BIG) asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(q.gb + addr));
-    else asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
     return v;
 }
 
@@ -263,22 +260,22 @@ __device__ __forceinline__ double2 ldrec(const LaneGeo& q, uint32_t addr) {
 // gO: Omega-half of this entry's gathered record on entry, of the next entry's on exit.
 // LIM: Taylor levels of y the entry may have (its record is zero beyond its own jm <= LIM): LIM = J+1 is the
 // complete product; smaller LIM drop the blocks of the absent levels at compile time and keep the load schedule.
-template <int J, bool BIG, int LIM>
+template <int J, int LIM>
 __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
                                             double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& wn,
                                             uint32_t& gp, uint32_t& yp, int& jm) {
     typedef RecGeom<J> R;
     double gD[2 * R::ND2];
 #pragma unroll
-    for (int u = 0; u < R::ND2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
+    for (int u = 0; u < R::ND2; ++u) { const double2 t = ldrec(q, gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
     uint32_t gp_n = gp, yp_n = yp;
     int jm_n = jm;
 #pragma unroll
     for (int k = 0; k < R::NPAD; ++k) {
         const double2 t = yq[k % R::YW];
         if (k == (R::NP1 > 1 ? 1 : 0)) decode_entry(q, wn, gp_n, yp_n, jm_n);   // after the first block has issued; before the next record is requested (J = 2: NP1 = 1)
-        if (k + R::YW < R::NPAD) yq[k % R::YW] = ldrec<BIG>(q, yp + 16 * R::unit(k + R::YW));
-        else yq[k % R::YW] = ldrec<BIG>(q, yp_n + 16 * R::unit(k + R::YW - R::NPAD));
+        if (k + R::YW < R::NPAD) yq[k % R::YW] = ldrec(q, yp + 16 * R::unit(k + R::YW));
+        else yq[k % R::YW] = ldrec(q, yp_n + 16 * R::unit(k + R::YW - R::NPAD));
         if (k >= R::NP) continue;   // padding pair
         if (k < R::NP1) {
             // conv(dA y, Omega g): y1[j1] times B1[j2] = gO[j2]
@@ -293,7 +290,7 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
             }
             if (k == R::NP1 - 1) {   // next entry's Omega-half lands while the d-half is consumed
 #pragma unroll
-                for (int u = 0; u < R::NO2; ++u) { const double2 g2 = ldrec<BIG>(q, gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
+                for (int u = 0; u < R::NO2; ++u) { const double2 g2 = ldrec(q, gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
             }
         } else {
             // conv(Omega y, dA g): y2[j1] times B2[j2] = gD[j2], j2 < J ; subtracted
@@ -314,7 +311,7 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
 // One list entry with only the first jm Taylor levels of y present (or, jm = J+2, a caller-supplied generator):
 // blocks run in ascending j1 and stop at the first absent level; y values are read on demand.  Keeps the
 // hand-over protocol of taylor_full (window and gO hold the next entry's data on exit).
-template <int J, bool BIG>
+template <int J>
 __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
                                                double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& wn,
                                                uint32_t& gp, uint32_t& yp, int& jm) {
@@ -322,7 +319,7 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     constexpr int JP = J + 1;
     double gD[2 * R::ND2];
 #pragma unroll
-    for (int u = 0; u < R::ND2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
+    for (int u = 0; u < R::ND2; ++u) { const double2 t = ldrec(q, gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
     uint32_t gp_n = gp, yp_n = yp;
     int jm_n = jm;
     decode_entry(q, wn, gp_n, yp_n, jm_n);
@@ -331,7 +328,7 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     for (int k = 0; k < R::NP1; ++k) {
         const int j1 = 2 * k;
         if (!(j1 + 1 < jm)) break;
-        const double2 t = (k < R::YW) ? yq[k] : ldrec<BIG>(q, yp + 16 * R::unit(k));
+        const double2 t = (k < R::YW) ? yq[k] : ldrec(q, yp + 16 * R::unit(k));
 #pragma unroll
         for (int j2 = 0; j2 <= J - j1; ++j2) acc[j1 + j2] = fma(t.x, gO[j2], acc[j1 + j2]);
         if (j1 + 1 < J && j1 + 2 < jm) {
@@ -341,18 +338,17 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     }
     if (JP < jm) {  // caller-supplied y with y1[J] != 0 (never on the fused path)
         double a;
-        if (BIG) asm volatile("ld.global.f64 %0, [%1];" : "=d"(a) : "l"(q.gb + yp + 8 * R::IDXJ));
-        else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(yp + 8 * R::IDXJ));
+        asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(yp + 8 * R::IDXJ));
         acc[J] = fma(a, gO[0], acc[J]);
     }
 #pragma unroll
-    for (int u = 0; u < R::NO2; ++u) { const double2 g2 = ldrec<BIG>(q, gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
+    for (int u = 0; u < R::NO2; ++u) { const double2 g2 = ldrec(q, gp_n + 16 * (R::ND2 + u)); gO[2 * u] = g2.x; gO[2 * u + 1] = g2.y; }
     // conv(Omega y, dA g): y2[j1] non-zero iff j1 < jm ; subtracted
 #pragma unroll
     for (int k = 0; k < R::NP2; ++k) {
         const int j1 = 2 * k;
         if (!(j1 < jm)) break;
-        const double2 t = (R::NP1 + k < R::YW) ? yq[R::NP1 + k] : ldrec<BIG>(q, yp + 16 * R::unit(R::NP1 + k));
+        const double2 t = (R::NP1 + k < R::YW) ? yq[R::NP1 + k] : ldrec(q, yp + 16 * R::unit(R::NP1 + k));
 #pragma unroll
         for (int j2 = 0; j2 < J && j1 + j2 <= J; ++j2) acc[j1 + j2] = fma(-t.x, gD[j2], acc[j1 + j2]);
         if (j1 + 1 <= J && j1 + 1 < jm) {
@@ -361,16 +357,16 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
         }
     }
 #pragma unroll
-    for (int k = 0; k < R::YW; ++k) yq[k] = ldrec<BIG>(q, yp_n + 16 * R::unit(k));
+    for (int k = 0; k < R::YW; ++k) yq[k] = ldrec(q, yp_n + 16 * R::unit(k));
     gp = gp_n; yp = yp_n; jm = jm_n;
 }
 
-template <int J, bool BIG>
+template <int J>
 __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, int e_end, double (&acc)[J + 1]) {
     typedef RecGeom<J> R;
     const DevPlan& P = RG_PLAN(c);
     const Sched& S = RG_SCHED(c);
-    const Smem sm = smem_view<BIG>(P, S, c);
+    const Smem sm = smem_view<false>(P, S, c);
     const uint2* const entries = S.entries;
     const int lane = threadIdx.x & 31;
     const uint32_t mc = S.lane_coord[box * 32 + lane];
@@ -380,15 +376,8 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     q.lim = 2u * (unsigned)P.L;
     q.zero_rec = P.M;
     q.rec_bytes = P.rec_units * 16;
-    if (BIG) {
-        q.gb = reinterpret_cast<const char*>(sm.G);
-        q.g_base = 0u;
-        q.y_base = (uint32_t)((P.M + RG_ZERO_RECS) * q.rec_bytes);
-    } else {
-        q.gb = nullptr;
-        q.g_base = (uint32_t)__cvta_generic_to_shared(sm.G);
-        q.y_base = (uint32_t)__cvta_generic_to_shared(sm.Y);
-    }
+    q.g_base = (uint32_t)__cvta_generic_to_shared(sm.G);
+    q.y_base = (uint32_t)__cvta_generic_to_shared(sm.Y);
     double gO[2 * R::NO2];
     double2 yq[R::YW];
 #pragma unroll
@@ -401,9 +390,9 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     int jm;
     decode_entry(q, entries[e_begin], gp, yp, jm);
 #pragma unroll
-    for (int u = 0; u < R::NO2; ++u) { const double2 t = ldrec<BIG>(q, gp + 16 * (R::ND2 + u)); gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
+    for (int u = 0; u < R::NO2; ++u) { const double2 t = ldrec(q, gp + 16 * (R::ND2 + u)); gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
 #pragma unroll
-    for (int k = 0; k < R::YW; ++k) yq[k] = ldrec<BIG>(q, yp + 16 * R::unit(k));
+    for (int k = 0; k < R::YW; ++k) yq[k] = ldrec(q, yp + 16 * R::unit(k));
     // The planner sorts a list by level class, so a piece is at most three runs: one tight loop per class (its
     // exit test uses the class of the NEXT entry, known since the decode early in the product) instead of a
     // dispatch chain per entry.  The outer loop only repeats if a list were not sorted.
@@ -414,25 +403,25 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
 #pragma unroll 1
         while (i < e_end && jm > J + 1) {           // caller-supplied y
             const uint2 wnn = entries[min(i + 2, last)];
-            taylor_partial<J, BIG>(acc, gO, yq, q, wn, gp, yp, jm);
+            taylor_partial<J>(acc, gO, yq, q, wn, gp, yp, jm);
             wn = wnn; ++i;
         }
 #pragma unroll 1
         while (i < e_end && jm <= J + 1 && jm > R::LIM_B) {
             const uint2 wnn = entries[min(i + 2, last)];
-            taylor_full<J, BIG, J + 1>(acc, gO, yq, q, wn, gp, yp, jm);
+            taylor_full<J, J + 1>(acc, gO, yq, q, wn, gp, yp, jm);
             wn = wnn; ++i;
         }
 #pragma unroll 1
         while (i < e_end && jm <= R::LIM_B && jm > R::LIM_A) {
             const uint2 wnn = entries[min(i + 2, last)];
-            taylor_full<J, BIG, R::LIM_B>(acc, gO, yq, q, wn, gp, yp, jm);
+            taylor_full<J, R::LIM_B>(acc, gO, yq, q, wn, gp, yp, jm);
             wn = wnn; ++i;
         }
 #pragma unroll 1
         while (i < e_end && jm <= R::LIM_A) {
             const uint2 wnn = entries[min(i + 2, last)];
-            taylor_full<J, BIG, R::LIM_A>(acc, gO, yq, q, wn, gp, yp, jm);
+            taylor_full<J, R::LIM_A>(acc, gO, yq, q, wn, gp, yp, jm);
             wn = wnn; ++i;
         }
     }
@@ -777,7 +766,7 @@ __device__ RG_CONV_ATTR void conv_all(Ctx& c) {
                         for (int j = 0; j < JP; ++j) acc[j] = om * S1[j] - (double)(j + 1) * S2[j];
                     }
                 } else {
-                    conv_piece<J, false>(c, p.x, p.y, p.z, acc);
+                    conv_piece<J>(c, p.x, p.y, p.z, acc);
                 }
                 if (lane == 0) {
                     if (st) while (vctl[nb_all] < need0) {}
