@@ -184,6 +184,11 @@ int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_t* iminus_w
                       int32_t** pieces, int32_t* n_entries, uint32_t** entries /*[n*2]*/,
                       int32_t* n_support, int32_t** supp_rec /*[M]*/, int64_t* cost, int32_t* n_stages,
                       int32_t* max_pieces);
+/* Run ends of every piece slot of that schedule: runs[slot][0] = end of the piece's run of complete Taylor products,
+   runs[slot][1] = end of its run truncated to LIM_B levels of y (the rest, to the piece's end, is truncated to LIM_A);
+   product_rule = 1 if the plan is costed for the product-rule form of the bracket (BIG kernels).  malloc'ed. */
+int rg_debug_piece_runs(int32_t dim, int32_t L, int32_t J, const uint8_t* iminus_wrapped, int32_t mode,
+                        int32_t** runs, int32_t* n_slots, int32_t* product_rule);
 void rg_debug_free(void* p);
 
 #ifdef __cplusplus

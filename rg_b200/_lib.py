@@ -67,6 +67,8 @@ SIGNATURES = {
                                          c_int_p, c_int_p, ctypes.POINTER(c_int_p), ctypes.POINTER(c_int_p), c_int_p,
                                          ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), c_int_p,
                                          ctypes.POINTER(c_int_p), ctypes.POINTER(ctypes.c_int64), c_int_p, c_int_p]),
+    "rg_debug_piece_runs": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, vp, ctypes.c_int32,
+                                           ctypes.POINTER(c_int_p), c_int_p, c_int_p]),
     "rg_debug_free": (None, [vp]),
 }
 

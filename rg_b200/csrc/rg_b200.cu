@@ -985,4 +985,20 @@ extern "C" int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_
     memcpy(*supp_rec, s.supp_rec.data(), sizeof(int32_t) * s.supp_rec.size());
     return 0;
 }
+// run ends of every piece slot of the same schedule ([n_stages * n_warps * max_pieces][2], aligned with `pieces` of
+// rg_debug_schedule) and whether the plan was costed for the product-rule form (BIG kernels)
+extern "C" int rg_debug_piece_runs(int32_t dim, int32_t L, int32_t J, const uint8_t* iminus_wrapped, int32_t mode,
+                                   int32_t** runs, int32_t* n_slots, int32_t* product_rule) {
+    if (dim < 1 || dim > 3 || J < 1 || J > 15 || L < 1 || !runs || !n_slots) return fail(-2, "bad geometry");
+    rgplan::Geometry g; g.init(dim, L, J);
+    std::vector<uint16_t> mask = masks_from_iminus(g, iminus_wrapped);
+    const bool big = needs_global_records(g, mask, RG_SMEM_OPTIN);
+    rgplan::Schedule s = rgplan::make_schedule(g, mask, mode == 1, mode == 2, rg_warps_for(g.M, g.J, big), 1, big);
+    if (s.n_warps < 0) return fail(-5, "too many output modes for one CTA's convolution schedule");
+    *n_slots = (int32_t)s.pieces.size();
+    if (product_rule) *product_rule = s.prule ? 1 : 0;
+    *runs = (int32_t*)malloc(sizeof(int32_t) * std::max<size_t>(s.piece_runs.size(), 1));
+    memcpy(*runs, s.piece_runs.data(), sizeof(int32_t) * s.piece_runs.size());
+    return 0;
+}
 extern "C" void rg_debug_free(void* p) { free(p); }

@@ -344,3 +344,36 @@ def test_plans_of_random_supports_cover_every_pair_once(dim, L, J):
         want = np.zeros((nout, M), dtype=int)
         want[:, supp] = need
         assert (visits == want).all(), (mode, int(np.abs(visits - want).sum()))
+
+
+@pytest.mark.parametrize("over,mode,big", [(dict(L=10, J=10), 2, 0), (dict(L=5, J=5), 0, 0), (dict(L=6, J=6, torus="spiral"), 2, 1),
+                                           (dict(L=6, J=6, torus="spiral"), 0, 1), (dict(L=20, J=4), 2, 1), (dict(L=4, J=2), 0, 0)])
+def test_piece_runs_are_class_sorted(over, mode, big):
+    """Every piece's list is sorted by level class -- complete products, then those truncated to LIM_B, then LIM_A -- and
+    the run ends the device loops use (rg_debug_piece_runs) cut it exactly there; plans of Hamiltonians too large for
+    the two-derivative records (n = 3 at L = J = 6; 2-D at L = 20, J = 4) are costed for the product-rule form."""
+    c = ro.OracleRG(ro.default_params(**over))
+    s = fetch_schedule(c, mode)
+    L_ = _lib.lib()
+    runs = ctypes.POINTER(ctypes.c_int32)()
+    n, pr = ctypes.c_int32(), ctypes.c_int32()
+    im = np.ascontiguousarray(c.Iminus.reshape(-1), dtype=np.uint8)
+    _lib.check(L_.rg_debug_piece_runs(c.dim, c.L, c.J, im.ctypes.data, int(mode), ctypes.byref(runs), ctypes.byref(n), ctypes.byref(pr)))
+    r = np.ctypeslib.as_array(runs, (n.value, 2)).copy()
+    L_.rg_debug_free(runs)
+    assert n.value == len(s["pieces"]) and pr.value == big
+    J = c.J
+    lim_a = 3 if J >= 8 else max(J // 2, 2)
+    lim_b = 6 if J >= 8 else J - 1
+    def cls(jm):
+        return J + 1 if jm > lim_b else (lim_b if jm > lim_a else lim_a)
+    seen = 0
+    for (box, b, e, rank), (e_full, e_mid) in zip(s["pieces"], r):
+        if box < 0:
+            continue
+        seen += 1
+        assert b <= e_full <= e_mid <= e
+        jm = (s["entries"][b:e, 0] >> 24).astype(int)
+        k = np.array([cls(v) for v in jm])
+        assert (k[:e_full - b] == J + 1).all() and (k[e_full - b:e_mid - b] == lim_b).all() and (k[e_mid - b:] == lim_a).all()
+    assert seen > 0

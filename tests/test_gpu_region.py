@@ -148,6 +148,32 @@ def test_every_taylor_order_has_a_kernel(J):
             os.environ.pop("RG_B200_FORCE_GLOBAL", None)
 
 
+@pytest.mark.parametrize("kind,L,J,xs,ys,g_smem,smem_max", [
+    ("golden", 20, 4, [0.01, 0.05], [0.02, 0.09], 1, 100000),      # 2-D beyond one SM: g-only records (81 KB) on chip
+    ("spiral", 8, 4, [0.005], [0.02, 0.25], 0, 232448)])           # 3-D, 4913 modes: even g-only records (236 KB) stay global
+def test_big_kernel_record_placements(kind, L, J, xs, ys, g_smem, smem_max):
+    """Hamiltonians beyond the two-derivative records of one SM run the BIG kernel (product-rule form of the bracket):
+    g records in shared memory when they fit, in the CTA's global workspace otherwise -- both against the CPU oracle."""
+    import rg_oracle as ro
+    from rg_b200 import RG, make_param_dict
+    from rg_b200.rg_dict import SPIRAL_MEAN
+    from rg_b200.rg_modules import region_maps
+    extra = dict(SPIRAL_MEAN) if kind == "spiral" else {}
+    c = RG(make_param_dict(L=L, J=J, CanonicalTransformation="expm_onestep", SaveData=False, **extra))
+    info_plan = c.plan_info()
+    out_bytes = (2 * L + 1) ** c.dim * (J + 1) * 8
+    assert (info_plan["smem_bytes"] < out_bytes) == bool(g_smem) and info_plan["smem_bytes"] <= smem_max
+    data, info = region_maps(c, np.array(xs), np.array(ys))
+    orc = ro.OracleRG(ro.default_params(L=L, J=J, CT="expm_onestep", **({"torus": "spiral"} if kind == "spiral" else {})))
+    oc, on, oe, _ = orc.region(np.array(xs), np.array(ys))
+    assert np.array_equal(data[:, :, 0], oc) and np.array_equal(data[:, :, 1], on) and np.array_equal(info, oe)
+    h = c.generate_1Hamiltonian([xs[0], ys[0]] + ([0.1] if kind == "spiral" else []), symmetric=True)
+    ho = orc.generate_1Hamiltonian([xs[0], ys[0]] + ([0.1] if kind == "spiral" else []), symmetric=True)
+    h, ho = c.rg_map(h), orc.rg_map(ho)
+    assert np.abs(h.f - ho.f).max() / np.abs(ho.f).max() < 1e-12
+    c.close()
+
+
 def test_J_out_of_range_is_rejected():
     from rg_b200 import _lib
     for J in (1, 13):
