@@ -923,7 +923,7 @@ __device__ RG_EPI_ATTR double2 series_epilogue_impl(Ctx& c, double* __restrict__
     const int dj = (int)blockDim.x / nmax, dnu = (int)blockDim.x - dj * nmax;
     int ja = (int)threadIdx.x / nmax, nua = (int)threadIdx.x - ja * nmax;
     for (int base = 0; base < total; base += CH * (int)blockDim.x) {
-        double v_[CH], fo_[CH];
+        double v_[CH], fo_[CH], om_[CH], w_[CH];
         int jb = ja, nub = nua;      // the write phase walks the same items again
 #pragma unroll
         for (int q = 0; q < CH; ++q) {
@@ -931,8 +931,13 @@ __device__ RG_EPI_ATTR double2 series_epilogue_impl(Ctx& c, double* __restrict__
             const int j = ja, nu = nua;
             ja += dj; nua += dnu;
             if (nua >= nmax) { nua -= nmax; ++ja; }
-            v_[q] = 0.0; fo_[q] = 0.0;
+            v_[q] = 0.0; fo_[q] = 0.0; om_[q] = 0.0; w_[q] = 1.0;
             if (i < total) {
+                // every global load of the item belongs to the read phase: behind the first store to f the compiler must
+                // assume aliasing, and a load issued between the stores waits out its own L2 round trip (the write phase
+                // used to load Omega_nu[nu] per item: 7 serialised round trips, 4 k of the epilogue's 6.8 k clocks)
+                if (!BIG) om_[q] = c.Omega_nu[nu];
+                if (!SUM && type == 3) w_[q] = P.normw[nu];
                 double dg;      // dA g  (RG.py:76)
                 if constexpr (BIG) {
                     const double* r = reinterpret_cast<const double*>(sm.G + nu * P.g_units);
@@ -963,8 +968,8 @@ __device__ RG_EPI_ATTR double2 series_epilogue_impl(Ctx& c, double* __restrict__
             if (i < total) {
                 const int mu = M - 1 - nu;
                 const bool twin = half && (mu != nu);
-                const double om = c.Omega_nu[nu];
-                const double w = (!SUM && type == 3) ? P.normw[nu] : 1.0;
+                const double om = om_[q];
+                const double w = w_[q];
                 const double v = v_[q], fn = fo_[q] + v;
                 f[j * M + nu] = fn;
                 norm_acc(type, ps, v, w);

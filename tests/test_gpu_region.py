@@ -161,8 +161,11 @@ def test_big_kernel_record_placements(kind, L, J, xs, ys, g_smem, smem_max):
     extra = dict(SPIRAL_MEAN) if kind == "spiral" else {}
     c = RG(make_param_dict(L=L, J=J, CanonicalTransformation="expm_onestep", SaveData=False, **extra))
     info_plan = c.plan_info()
-    out_bytes = (2 * L + 1) ** c.dim * (J + 1) * 8
-    assert (info_plan["smem_bytes"] < out_bytes) == bool(g_smem) and info_plan["smem_bytes"] <= smem_max
+    M = (2 * L + 1) ** c.dim
+    g_units = (J + 2) // 2 + (1 - ((J + 2) // 2) % 2)            # g[0..J] in 16-byte units, made odd
+    fixed = 64 * 8 + 16 + 128 * 16                               # reduction scratch, ticket, control block
+    want = (M + 8) * g_units * 16 + fixed if g_smem else M * (J + 1) * 8 + fixed
+    assert info_plan["smem_bytes"] == want and want <= smem_max, (info_plan["smem_bytes"], want)
     data, info = region_maps(c, np.array(xs), np.array(ys))
     orc = ro.OracleRG(ro.default_params(L=L, J=J, CT="expm_onestep", **({"torus": "spiral"} if kind == "spiral" else {})))
     oc, on, oe, _ = orc.region(np.array(xs), np.array(ys))
