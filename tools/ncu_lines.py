@@ -9,23 +9,31 @@ sub = sys.argv[2] if len(sys.argv) > 2 else "rg_kernelILi10ELb0"
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tmp = tempfile.mkdtemp()
-subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(root, "rg_b200", "librg_b200.so")], cwd=tmp, capture_output=True)
-cubin = [os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
-lines, cur, on = [], None, False
-for l in dis:
-    if l.startswith(".text."):
-        on = sub in l
-        continue
-    if not on:
-        continue
-    m = re.search(r'//## File "(.*)", line (\d+)', l)
-    if m:
-        cur = (os.path.basename(m.group(1)), int(m.group(2)))
-        continue
-    m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(\S.*);", l)
-    if m:
-        lines.append((int(m.group(1), 16), cur, m.group(2)))
+# every Taylor order is its own translation unit: take the object of the profiled instantiation (the cubins inside the
+# linked library all carry the same name and overwrite each other on extraction)
+mo = re.search(r"rg_kernelILi(\d+)ELb(\d)", sub)
+obj = os.environ.get("NCU_LINES_OBJ") or (os.path.join(root, "rg_b200", "csrc", "build", "inst_%s_%s.o" % (mo.group(1), mo.group(2)))
+                                           if mo else os.path.join(root, "rg_b200", "librg_b200.so"))
+subprocess.run(["cuobjdump", "-xelf", "all", obj], cwd=tmp, capture_output=True)
+lines = []
+for cubin in sorted(os.path.join(tmp, f) for f in os.listdir(tmp) if f.endswith(".cubin")):   # one cubin per translation unit
+    dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+    cur, on = None, False
+    for l in dis:
+        if l.startswith(".text."):
+            on = sub in l
+            continue
+        if not on:
+            continue
+        m = re.search(r'//## File "(.*)", line (\d+)', l)
+        if m:
+            cur = (os.path.basename(m.group(1)), int(m.group(2)))
+            continue
+        m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(\S.*);", l)
+        if m:
+            lines.append((int(m.group(1), 16), cur, m.group(2)))
+    if lines:
+        break
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 h = next(i for i, r in enumerate(rows) if "Source" in r)
