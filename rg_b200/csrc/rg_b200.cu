@@ -290,7 +290,7 @@ static int dev_upload(rg_plan* p, const T* host, size_t n, T** out) {
 static int rg_warps_for(int M, int J, bool big = false) {
     int w = (((M + 31) / 32 + 3) / 4) * 4;
     if (w < 4) w = 4;
-    const int wmax = (J >= 8 || big) ? 12 : 8;   // must match __launch_bounds__ of rg_kernel<J, BIG>: 384 x 168 regs, or 256 x 128
+    const int wmax = big ? 12 : 8;   // must match rgdev::KernelShape: BIG 384 x 168 registers; else 256 x 255 (J >= 8) or 256 x 128
     if (w > wmax) w = wmax;
     const char* e = getenv("RG_B200_WARPS");
     if (e && atoi(e) >= 4 && atoi(e) <= wmax && atoi(e) % 4 == 0) w = atoi(e);
