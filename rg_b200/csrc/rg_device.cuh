@@ -22,7 +22,8 @@ struct Sched {
     const uint32_t* lane_coord;  // [NB*32] packed biased coords
     const int4* pieces;          // [n_stages][NW*maxp] {box, begin, end, rank}; box = -1 unused; heads first
     const int2* piece_runs;      // same shape: {end of the piece's run of complete products, end of its run truncated to LIM_B}
-    const uint2* entries;        // {packed coords of nu1, (rec<<8)|jm}
+    const uint2* entries;        // word 0: packed biased coords of nu1 | jm<<24 -- BIG kernels: the lanes of the box in range for nu1
+                                 // (bit l = lane l); word 1: centred index of nu1 | rec<<16
     const int* supp_rec;         // [M] record of centred mode or -1
 };
 
@@ -472,26 +473,25 @@ struct RecGeomPR {
     static constexpr int YREGS = YALL ? NPMAX : 1;
 };
 
-// Per-lane constants of the gather: biased coords of the lane's output mode, its linear index, limits.
+// Per-lane constants of the gather: the lane's bit in an entry's range mask, the linear index of its output mode.
 struct LaneGeoPR {
-    int v0, v1, v2;       // coords + L  (so that v - e, e = biased coord of nu1, is the biased coord of nu - nu1)
+    uint32_t lanebit;     // 1 << lane
     int lin;              // sum_d v_d * stride_d : centred index of (nu - nu1) = lin - index(nu1)
-    unsigned lim;         // 2L
     int zero_rec;         // index of the first all-zero record (M)
     int g_bytes, y_bytes;     // record strides
     const char* gg;           // the g records: a generic pointer (shared memory when they fit, else the CTA's workspace)
     const char* gy;           // the Y records: the CTA's global workspace
 };
 
-// next entry: test nu - nu1 against the grid, form the two record addresses.  w = the entry's two list words, read
-// by every lane from the same address two entries ahead (a warp-wide block of words broadcast by SHFL put the
-// shuffle's latency on the critical path of the short, level-truncated products: 6 % of the stall samples).
+// next entry: form the two record addresses.  w = the entry's two list words, read by every lane from the same address
+// two entries ahead.  Whether nu - nu1 is on the grid is the planner's test in these kernels: word 0 carries one bit per
+// lane of the box (an integer instruction costs the fp64 stream an issue cycle and the DFMA behind it its operand-reuse
+// hit, tools/dfma_lab; the three-coordinate test was 9 of them per entry: bracket of config 5 1.120 M -> 1.067 M clocks.
+// The shared-memory kernels keep the test: there ptxas turned the shorter decode into a slower schedule, +1.9 %).
 // An out-of-range lane gathers the zero record congruent (mod 8) to the record it would have read.
 __device__ __forceinline__ void decode_entry_pr(const LaneGeoPR& q, const uint2& w, uint32_t& gp, uint32_t& yp, int& nat_out) {
-    const uint32_t ec = w.x, ei = w.y;
-    const unsigned u0 = (unsigned)(q.v0 - (int)(ec & 0xff)), u1 = (unsigned)(q.v1 - (int)((ec >> 8) & 0xff)),
-                   u2 = (unsigned)(q.v2 - (int)((ec >> 16) & 0xff));
-    const bool ok = max(max(u0, u1), u2) <= q.lim;
+    const uint32_t ei = w.y;
+    const bool ok = (w.x & q.lanebit) != 0;
     const int nat = q.lin - (int)(ei & 0xffff);
     const int gi = ok ? nat : q.zero_rec + ((nat - q.zero_rec) & (RG_ZERO_RECS - 1));
     gp = (uint32_t)(gi * q.g_bytes);
@@ -622,9 +622,8 @@ __device__ __forceinline__ LaneGeoPR lane_geometry_pr(const Ctx& c, int box) {
     const int lane = threadIdx.x & 31;
     const uint32_t mc = S.lane_coord[box * 32 + lane];
     LaneGeoPR q;
-    q.v0 = (int)(mc & 0xff) + P.L; q.v1 = (int)((mc >> 8) & 0xff) + P.L; q.v2 = (int)((mc >> 16) & 0xff) + P.L;
-    q.lin = q.v0 * P.stride0 + q.v1 * P.stride1 + q.v2 * P.stride2;
-    q.lim = 2u * (unsigned)P.L;
+    q.lanebit = 1u << lane;
+    q.lin = ((int)(mc & 0xff) + P.L) * P.stride0 + ((int)((mc >> 8) & 0xff) + P.L) * P.stride1 + ((int)((mc >> 16) & 0xff) + P.L) * P.stride2;
     q.zero_rec = P.M;
     q.g_bytes = P.g_units * 16;
     q.y_bytes = P.rec_units * 16;

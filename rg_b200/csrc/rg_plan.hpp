@@ -110,7 +110,9 @@ struct Schedule {
     std::vector<int32_t> piece_runs;   // [n_stages][NW*maxp][2]: end of the piece's run of complete products, end of its LIM_B run
     bool general = false;              // caller-supplied generator (dense): every entry takes the general product
     bool prule = false;                // costs counted for the product-rule form of the bracket (BIG kernels)
-    std::vector<uint32_t> entries;     // [n*2]: {biased coords of nu1 (8 bits each) | jm<<24, centred index | rec<<16}
+    std::vector<uint32_t> entries;     // [n*2]: {biased coords of nu1 (8 bits each) | jm<<24 -- prule: lanes of the piece's box whose nu - nu1 is
+                                       // on the grid (bit l = lane l), centred index of nu1 | rec<<16}
+    std::vector<uint8_t> entry_jm;     // [n]: Taylor levels of y present at the entry's nu1 (J+2: caller-supplied generator)
     std::vector<int32_t> supp_rec;     // [M] record index of centred nu1, -1 if not in support
     std::vector<uint8_t> jm;           // [M] 1 + highest I^- level (0 = not in support)
     int64_t fma_useful = 0;            // per liouville, in-range & structurally non-zero
@@ -234,17 +236,19 @@ inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t
         }
         return order;
     };
-    auto valid_lanes = [&](const std::vector<int>& order, int b, int c1) {
+    // lanes of box b (bit l = lane l) whose output mode nu has nu - nu1 on the grid
+    auto valid_mask = [&](const std::vector<int>& order, int b, int c1) {
         int v1[4]; g.coords(c1, v1);
-        int nvalid = 0;
+        uint32_t m = 0;
         for (int l = 0; l < 32 && b * 32 + l < NO; ++l) {
             int v[4]; g.coords(order[b * 32 + l], v);
             bool ok = true;
             for (int d = 0; d < g.dim; ++d) { int u = v[d] - v1[d] + L; if (u < 0 || u > 2 * L) ok = false; }
-            nvalid += ok;
+            if (ok) m |= 1u << l;
         }
-        return nvalid;
+        return m;
     };
+    auto valid_lanes = [&](const std::vector<int>& order, int b, int c1) { return __builtin_popcount(valid_mask(order, b, c1)); };
     std::vector<std::vector<int>> orders;
     std::vector<int> stage_of(M, 0);
     const bool two_stage = (allow_two_stage && (g.dim == 2 || g.dim == 3) && csize == 1 && NBS >= 2);
@@ -360,10 +364,13 @@ inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t
                     while (k < lists[b].size()) {
                         const int c1 = lists[b][k];
                         if (w < w1 - 1 && acc * NWc >= gtotal * (int64_t)(w - w0 + 1) && (int)s.entries.size() / 2 > pc.begin) break;
+                        // word0: biased coords of nu1 (the kernel's range test) | jm<<24 -- product-rule form (BIG kernels):
+                        // the lanes in range (the test is the planner's; the level class is in the piece's run ends);
+                        // word1: centred linear index | record<<16
                         int v1[4]; g.coords(c1, v1);
-                        // word0: biased coords (validity test) | jm<<24 ; word1: centred linear index | record<<16
-                        s.entries.push_back(g.pack(v1) | ((uint32_t)s.jm[c1] << 24));
+                        s.entries.push_back(prule ? valid_mask(order, b, c1) : (g.pack(v1) | ((uint32_t)s.jm[c1] << 24)));
                         s.entries.push_back((uint32_t)c1 | ((uint32_t)s.supp_rec[c1] << 16));
+                        s.entry_jm.push_back(s.jm[c1]);
                         acc += wcost_of(c1); wcost[w] += wcost_of(c1);
                         ++k;
                     }
@@ -392,7 +399,7 @@ inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t
         const Piece& pc = s.pieces[i];
         if (pc.box < 0) continue;
         int e_full = pc.begin, e_mid;
-        auto cls = [&](int e) { return level_class((int)(s.entries[2 * (size_t)e] >> 24), J); };
+        auto cls = [&](int e) { return level_class((int)s.entry_jm[(size_t)e], J); };
         const int lim_a = (J >= 8) ? 3 : (J / 2 > 2 ? J / 2 : 2), lim_b = (J >= 8) ? 6 : J - 1;   // as in level_class
         while (e_full < pc.end && cls(e_full) > std::max(lim_a, lim_b)) ++e_full;    // complete products (and the general ones)
         e_mid = e_full;

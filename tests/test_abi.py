@@ -99,6 +99,15 @@ def fetch_schedule(c, mode):
                supp=np.ctypeslib.as_array(supp, (M,)).copy())
     for p in (lane_out, pieces, entries, supp):
         L_.rg_debug_free(p)
+    # Taylor levels of y present per centred mode (1 + highest I^- level, 0 = not in the support; dense: J + 2)
+    im_c = np.roll(c.Iminus, c.dim * (c.L,), axis=tuple(range(1, c.dim + 1))).reshape(c.J + 1, -1)
+    jm = np.where(im_c.any(axis=0), c.J + 1 - np.argmax(im_c[::-1], axis=0), 0)
+    out["jm"] = np.full(M, c.J + 2) if mode == 1 else jm
+    # word 0 of an entry: biased coords of nu1 | jm<<24, or -- plans of the product-rule form (BIG kernels) -- the range mask
+    runs, nslots, pr = ctypes.POINTER(ctypes.c_int32)(), ctypes.c_int32(), ctypes.c_int32()
+    _lib.check(L_.rg_debug_piece_runs(c.dim, c.L, c.J, im.ctypes.data, int(mode), ctypes.byref(runs), ctypes.byref(nslots), ctypes.byref(pr)))
+    L_.rg_debug_free(runs)
+    out["prule"] = bool(pr.value)
     return out
 
 
@@ -139,15 +148,20 @@ def replay(c, sched, y1, y2, g, Omega_nu):
             lanes = sched["lane_out"][box * 32:(box + 1) * 32]
             acc = np.zeros((32, J + 1))
             for ent in sched["entries"][b:e]:
-                ec = [(int(ent[0]) >> (8 * d)) & 0xff for d in range(dim)]
-                jm, rec = int(ent[0]) >> 24, int(ent[1]) >> 16
+                mask, rec = int(ent[0]), int(ent[1]) >> 16
                 nu1 = nu_of_rec[rec]
-                assert list(coords[nu1]) == ec and (int(ent[1]) & 0xffff) == nu1
+                assert (int(ent[1]) & 0xffff) == nu1
+                jm = int(sched["jm"][nu1])
+                if not sched["prule"]:
+                    assert [(mask >> (8 * d)) & 0xff for d in range(dim)] == list(coords[nu1]) and mask >> 24 == jm
                 for l, nu in enumerate(lanes):
                     if nu < 0:
+                        assert not (sched["prule"] and (mask >> l) & 1), "an idle lane is never in range"
                         continue
                     u = coords[nu] - coords[nu1] + L
-                    gi = int((u * strides).sum()) if ((u >= 0) & (u <= 2 * L)).all() else M
+                    ok = bool(((u >= 0) & (u <= 2 * L)).all())
+                    assert not sched["prule"] or ok == bool((mask >> l) & 1), "word 0 of an entry is the box's range mask"
+                    gi = int((u * strides).sum()) if ok else M
                     for j1 in range(J + 1):
                         if j1 + 1 < jm:                  # y1[j1] = (j1+1) y[j1+1]; jm = J+2 keeps a caller's y1[J]
                             a = Y1[nu1, j1]
@@ -259,6 +273,15 @@ def test_schedule_geometry_config5():
             have = set()
             for _, b, e in seen.get(box, []):
                 have |= set((s["entries"][b:e, 1] & 0xffff).astype(int))
+                # product-rule plans: word 0 of an entry is the range mask of this box's 32 lanes (the kernel has no test)
+                assert s["prule"]
+                all_l = lanes[box * 32:(box + 1) * 32]
+                act = all_l >= 0
+                v1 = (s["entries"][b:e, 1] & 0xffff).astype(int)
+                uu = coords[np.where(act, all_l, 0)][:, None, :] - coords[v1][None, :, :] + L       # [lane, entry, d]
+                ok = ((uu >= 0) & (uu <= 2 * L)).all(axis=2) & act[:, None]
+                want_mask = (ok.astype(np.uint64) << np.arange(32, dtype=np.uint64)[:, None]).sum(axis=0).astype(np.uint32)
+                assert np.array_equal(want_mask, s["entries"][b:e, 0].astype(np.uint32)), (box, b, e)
             assert have == set(supp[need & mine]), box
         cost[mode] = s["cost"]
         assert s["cost"][0] / s["cost"][1] > 0.57, "two partitions + level classes: useful/issued = lane efficiency (0.65) x 54/60 (this size runs the BIG kernel: product-rule form, 60 DFMAs per complete pair at J = 6 for 54 algorithmic ones)"
@@ -380,7 +403,7 @@ def test_piece_runs_are_class_sorted(over, mode, big):
             continue
         seen += 1
         assert b <= e_full <= e_mid <= e
-        jm = (s["entries"][b:e, 0] >> 24).astype(int)
+        jm = s["jm"][(s["entries"][b:e, 1] & 0xffff).astype(int)]
         k = np.array([cls(v) for v in jm])
         assert (k[:e_full - b] == J + 1).all() and (k[e_full - b:e_mid - b] == lim_b).all() and (k[e_mid - b:] == lim_a).all()
     assert seen > 0

@@ -388,6 +388,22 @@ def schedule(block, verbose=False):
     max_wait = int(os.environ.get('SCHED_MAXWAIT', '0'))
     window = int(os.environ.get('SCHED_WINDOW', '40'))
     load_delay = int(os.environ.get('SCHED_LOADDELAY', '3'))
+    rank_policy = os.environ.get('SCHED_RANK', '0') == '1'
+    local_mode = os.environ.get('SCHED_LOCAL', '0') == '1'
+    run_of, r_ = {}, 0
+    for x in body:
+        if x.dfma:
+            run_of[x] = r_
+        else:
+            r_ += 1
+    rank_slack = int(os.environ.get('SCHED_RANKSLACK', '4'))
+    rank, k_ = {}, 0
+    for x in body:
+        if x.dfma:
+            k_ += 1
+        else:
+            rank[x] = k_
+    n_out = [0]
     ready_for = 0
 
     remaining = set(D)
@@ -415,6 +431,7 @@ def schedule(block, verbose=False):
                 ready_d.add(s)
         if x.dfma:
             ready_d.discard(x); remaining.discard(x)
+            n_out[0] += 1
 
     def shares(x, y):
         """(slot of x, slot of y) of a common multiplicand register, or None"""
@@ -435,18 +452,23 @@ def schedule(block, verbose=False):
         # are only regrouped inside a window of the original order, else a row pulled far forward meets its operands
         # still in flight and a row left far behind holds up the load that recycles its registers.
         horizon = (min(x.pos for x in remaining) + window) if remaining else 0
+        if local_mode and remaining:
+            # only the DFMAs of the current run (between two non-DFMA instructions of the original order) may be picked
+            cur_run = min(run_of[x] for x in remaining)
+            horizon = max(x.pos for x in remaining if run_of[x] == cur_run)
         # DFMAs the next loads wait for (they still read what those loads overwrite) go first; a load that has been
         # ready for more than `load_delay` DFMAs ends the row (a broken chain costs a cycle, an operand in flight tens)
         urgent = set()
         for L in lq[:2]:
             urgent |= {p for p in preds[L] if p.dfma and p not in emitted}
-        if lq and npred[lq[0]] == 0:
+        if lq and npred[lq[0]] == 0 and not (rank_policy and n_out[0] < rank[lq[0]] - rank_slack):
             ready_for += 1
         else:
             ready_for = 0
+        at_rank = local_mode and any(q and q[0] is not bra and npred[q[0]] == 0 and rank[q[0]] == n_out[0] for q in (lq, aq))
         # 1. continue the chain
         best = None
-        if last_d is not None and ready_for <= load_delay:
+        if last_d is not None and ready_for <= load_delay and not at_rank:
             cands = []
             for x in ready_d:
                 if x.pos > horizon:
@@ -481,6 +503,10 @@ def schedule(block, verbose=False):
             for q in (lq, aq):
                 while q and npred[q[0]] == 0 and q[0] is not bra:
                     y = q[0]
+                    if rank_policy and remaining and n_out[0] < rank[y] - rank_slack:
+                        break      # stays near its original place in the DFMA stream (its lead time is ptxas's)
+                    if local_mode and (n_out[0] != rank[y] or (lq and aq and min(lq[0].pos, aq[0].pos) != y.pos)):
+                        break      # exactly its original place, original order among the non-DFMA instructions
                     w = lat_wait(y, tnow)
                     if (w > max_wait and ready_d) or (w > 0 and not order):   # nothing can delay the first instruction
                         break
