@@ -63,6 +63,15 @@ def test_approach_batch_matches_host_bisection():
         host = c.approach(p, reldist=1e-6)
         for a, b in zip(host, d):
             assert np.array_equal(a.f, b.f) and a.count == b.count and a.error == b.error
+    # ... and against the oracle's bisection (RG.py:292-307 restated on the CPU): the same bracketing pair.  The midpoints
+    # are exact averages, so the two bisections agree bit for bit as long as every converge() gives the same verdict; a
+    # midpoint on the critical surface itself may be decided either way, which moves a bracket end by at most RelDist
+    import rg_oracle as ro
+    orc = ro.OracleRG(ro.default_params(L=5, J=5, CT="expm_onestep"))
+    for p, d in zip(pairs, dev):
+        want = orc.approach([ro.Hamiltonian(h.Omega, h.f.copy()) for h in p], 1e-6)
+        for a, b in zip(want, d):
+            assert np.abs(a.f - b.f).max() <= 2e-6 * np.abs(a.f).max(), "device bisection left the oracle's bracket"
     c.close()
 
 
