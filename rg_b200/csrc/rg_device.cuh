@@ -829,7 +829,7 @@ __device__ __noinline__ void build_G(const Ctx& c, const double* __restrict__ sr
     const int M = P.M;
     const Smem sm = smem_view<BIG>(P, RG_SCHED(c), c);
     // exactly symmetric src (c.symm): the thread of nu <= 0 also writes the mirror record (one pass over 221 of the
-    // 441 modes at L = 10 instead of two passes of 384 + 57 threads)
+    // 441 modes at L = 10 in one pass of the CTA's threads)
     const bool mirror = c.symm != 0;
     const int nmax = mirror ? (M + 1) / 2 : M;
     for (int nu = threadIdx.x; nu < nmax; nu += blockDim.x) {
@@ -915,7 +915,7 @@ __device__ RG_EPI_ATTR double2 series_epilogue_impl(Ctx& c, double* __restrict__
     const long long t_begin = clock64();
     double ps = 0.0, pf = 0.0;
     // Work item = one coefficient (j, nu), j-major, dealt round-robin to ALL threads of the CTA (a thread per mode
-    // would leave 5 of 12 warps idle on the half-space schedule and serialise 11 levels per thread).  The new
+    // would leave 40 % of the warps idle on the half-space schedule and serialise 11 levels per thread).  The new
     // d-type entry r[j-1] = j*sh[j] overwrites what item (j-1, nu) reads as dA g: items are processed in chunks of
     // CH per thread, reads first, a barrier, then the writes; (j-1, nu) is in the same or an earlier chunk.
     // (j, nu) of item i = base + q*blockDim + tid, advanced without divisions

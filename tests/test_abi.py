@@ -334,6 +334,37 @@ def test_sass_tune_round_trip(tmp_path):
     assert re.search(r"sass_tune: 0 DFMA retuned", r3.stdout), r3.stdout
 
 
+def test_hot_loop_canary():
+    """ptxas allocates the hot loop of conv_all together with the rest of the kernel: an edit anywhere in rg_device.cuh can
+    change its schedule by several per cent either way (the epilogue's chunk size moved the bracket from 107 k to
+    117 k clocks).  Static canary on the built L=J=10 object: the complete-product loop body has 130 DFMAs, no more than 60
+    other instructions, no spills, a stall-count sum below 300 cycles and -- in the linked, retuned library -- at least 64
+    adjacent operand-reuse hits.  A failure here means: measure before committing."""
+    import shutil
+    import sys
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_sched as S
+
+    def main_block(path):
+        funcs = S.disassemble(path, "rg_kernelILi10ELb0")
+        blocks = [b for insts in funcs.values() for b in S.hot_blocks(insts)]
+        full = [b for b in blocks if sum(1 for r in b if r[1].startswith("DFMA ")) == 130]
+        assert len(full) == 1, [len(b) for b in blocks]
+        ins = [S.parse(*r) for r in full[0]]
+        hits = 0
+        for p, x in zip(ins, ins[1:]):
+            if p.dfma and x.dfma and any((p.hi >> (57 + s)) & 1 and S.dfma_key(p, s) == S.dfma_key(x, s) for s in (1, 2)):
+                hits += 1
+        return ins, hits
+    ins, hits = main_block(_lib.SO_PATH)
+    assert len(ins) - 130 <= 60, len(ins)
+    assert sum(max(x.stall, 1) for x in ins) < 300
+    assert not any(x.op.startswith(("LDL", "STL")) for x in ins), "the hot loop spills"
+    assert hits >= 64, hits
+
+
 def test_sass_sched_study_tool_keeps_its_hazard_rules(tmp_path):
     """tools/sass_sched.py (a study, not part of the build: DESIGN 4.1) on a copy of the L=J=10 object: it regroups the DFMAs
     of the four hot loop bodies, its independent hazard pass finds nothing (scoreboard waits, covered loads, fixed latencies,
