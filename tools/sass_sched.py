@@ -1,4 +1,16 @@
-"""Post-link instruction scheduling of the DFMA loops of rg_kernel (sm_100a): same instructions, better order.
+"""Post-link instruction scheduling of the DFMA loops of rg_kernel (sm_100a): same instructions, another order.
+
+STATUS: a study, not part of the build (the Makefile runs rg_b200/csrc/sass_tune.py only).  Measured on B200
+(profiles/probe_r02_sass_sched_*.log, probe_r02_8warps_sched_and_4warps.log): the regrouped loop has up to
+113 instead of ~63 adjacent operand-reuse hits per list entry and runs 8.7 % faster in isolation (tools/half_lane_bench),
+but inside the kernel it gains no more than the flag retune of sass_tune.py (12 warps: -2.5 % both) and loses against it
+with the shipped 8 warps x 253 registers (61.9 against 58.9 ms): every regrouping moves some shared-memory load closer to
+its consumer, and ncu shows the fp64-pipe stalls it removes coming back as scoreboard stalls.  Kept because its hazard
+rules (below) are the record of what the hardware needs from a scheduler, and tests/test_abi.py checks them.
+Policy knobs (environment): SCHED_STRICT=1 (non-DFMA instructions keep their total order), SCHED_WINDOW (how far a DFMA may
+move ahead of the oldest unplaced one, in instructions), SCHED_MAXWAIT, SCHED_LOADDELAY, SCHED_RANK / SCHED_RANKSLACK
+(non-DFMA instructions stay near their original rank in the DFMA stream), SCHED_LOCAL=1 (DFMAs only permute between two
+non-DFMA instructions), SCHED_CAP, SCHED_YIELD, SCHED_BURST.
 
 Why.  The bracket's inner loops are long streams of DFMAs (acc[j1+j2] += y[j1] * g[j2]) with the loads and the decode of
 the next list entry mixed in.  Measured on B200 with hand-patched instruction streams (tools/dfma_lab):
