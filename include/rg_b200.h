@@ -178,10 +178,9 @@ int rg_pnorm(rg_plan* plan, int32_t n, const double* y0, const double* y1, const
    rg_debug_free.  A schedule has n_stages (1 or 2) stages, each a partition of the output modes into boxes
    (stage 0 stores, stage 1 adds).  pieces: [n_stages][n_warps*max_pieces][4] = {box, begin, end, rank}, box = -1
    unused (max_pieces = piece slots per warp: 4, more when a warp has to own many boxes).
-   entries: [n][2] list words: word 1 = centred index of the source mode nu1 | its record << 16; word 0 = its biased
-   coordinates (8 bits each) | Taylor levels present << 24, or -- plans of the product-rule form (Hamiltonians too large
-   for one SM's shared memory, rg_debug_piece_runs' product_rule = 1) -- the lanes of the piece's box whose nu - nu1 is
-   on the grid (bit l = lane l).
+   entries: [n][2] list words: word 0 = the lanes of the piece's box whose nu - nu1 is on the grid (bit l = lane l: the
+   range test of the truncated convolution is the planner's, the kernels only test their bit); word 1 = centred index of
+   the source mode nu1 | its record << 16.
    cost[4] = {useful FMAs, issued FMAs (32 lanes x list cost), max per-warp list cost, total list cost}. */
 int rg_debug_schedule(int32_t dim, int32_t L, int32_t J, const uint8_t* iminus_wrapped, int32_t mode,
                       int32_t* n_warps, int32_t* n_boxes, int32_t** lane_out /*[NB*32] centred idx*/,

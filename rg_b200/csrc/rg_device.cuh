@@ -22,8 +22,7 @@ struct Sched {
     const uint32_t* lane_coord;  // [NB*32] packed biased coords
     const int4* pieces;          // [n_stages][NW*maxp] {box, begin, end, rank}; box = -1 unused; heads first
     const int2* piece_runs;      // same shape: {end of the piece's run of complete products, end of its run truncated to LIM_B}
-    const uint2* entries;        // word 0: packed biased coords of nu1 | jm<<24 -- BIG kernels: the lanes of the box in range for nu1
-                                 // (bit l = lane l); word 1: centred index of nu1 | rec<<16
+    const uint2* entries;        // {lanes of the box in range for nu1 (bit l = lane l), centred index of nu1 | rec<<16}
     const int* supp_rec;         // [M] record of centred mode or -1
 };
 
@@ -193,14 +192,14 @@ struct RecGeom {
     static constexpr int NP1 = (J + 1) / 2;   // y pairs of conv(dA y, Omega g): y1[0..J-1]
     static constexpr int NP2 = J / 2 + 1;     // y pairs of conv(Omega y, dA g): y2[0..J]
     static constexpr int NP = NP1 + NP2;
-    // prefetch window (pairs).  1 is the measured optimum (uniform batch, L=J=10: 50.0 ms against 50.4 / 50.8 / 52.7 ms
-    // with a window of 2 / 3 / 4): a short window leaves ptxas's list scheduler fewer independent rows to interleave, so
-    // more consecutive DFMAs share the broadcast y operand through the operand-reuse cache (a DFMA with three fresh
-    // 64-bit operands holds the fp64 pipe 3 cycles instead of 2); the other warps of the sub-partition cover the
-    // shared-memory latency.  Forcing the loads into source order (ld.volatile) spreads them perfectly and is 9 % slower:
-    // the reuse hits, not the load latency, decide (tools/sass_reuse.py counts them in a SASS listing).
+    // prefetch window of the broadcast y values (pairs).  Which window is best is a property of the register allocation
+    // ptxas settles on for the whole kernel, not of the loop: with 12 warps x 168 registers and the coordinate
+    // test in the decode 1 pair won (50.0 ms on the uniform batch against 50.4 / 50.8 / 52.7 ms with 2 / 3 / 4), with the
+    // shipped 8 warps x 255 registers and the planner's range masks 3 pairs do (57.4 ms against 60.0 with 1, 58.4 with 2):
+    // the candidates were ranked on the CPU by the measured DFMA cost model (2 cycles with an adjacent operand-reuse hit,
+    // 3 without, +1 per integer instruction; tools/dfma_lab) and the best three confirmed on the GPU.
 #ifndef RG_YW
-#define RG_YW 1
+#define RG_YW ((J >= 8) ? 3 : 1)
 #endif
     static constexpr int YW = RG_YW;
     // Every entry runs a branch-free, software-pipelined Taylor product on its zero-padded y record (the absent
@@ -224,25 +223,23 @@ __device__ __forceinline__ void load_d_half(double (&gD)[2 * RecGeom<J>::ND2], c
     for (int u = 0; u < RecGeom<J>::ND2; ++u) { const double2 t = gp[u]; gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
 }
 
-// Per-lane constants of the gather: biased coords of the lane's output mode, its linear index, limits.
+// Per-lane constants of the gather: the lane's bit in an entry's range mask, the linear index of its output mode.
 struct LaneGeo {
-    int v0, v1, v2;       // coords + L  (so that v - e, e = biased coord of nu1, is the biased coord of nu - nu1)
+    uint32_t lanebit;     // 1 << lane
     int lin;              // sum_d v_d * stride_d : centred index of (nu - nu1) = lin - index(nu1)
-    unsigned lim;         // 2L
     int zero_rec;         // index of the first all-zero record (M)
     uint32_t g_base, y_base;  // shared-memory byte addresses of G and Y
     int rec_bytes;
 };
 
-// next entry: test nu - nu1 against the grid, form the two record addresses.  w = the entry's two list words, read
-// by every lane from the same address two entries ahead (a warp-wide block of words broadcast by SHFL put the
-// shuffle's latency on the critical path of the short, level-truncated products: 6 % of the stall samples).
-__device__ __forceinline__ void decode_entry(const LaneGeo& q, const uint2& w, uint32_t& gp, uint32_t& yp, int& jm) {
-    const uint32_t ec = w.x, ei = w.y;
-    jm = (int)(ec >> 24);
-    const unsigned u0 = (unsigned)(q.v0 - (int)(ec & 0xff)), u1 = (unsigned)(q.v1 - (int)((ec >> 8) & 0xff)),
-                   u2 = (unsigned)(q.v2 - (int)((ec >> 16) & 0xff));
-    const bool ok = max(max(u0, u1), u2) <= q.lim;
+// next entry: form the two record addresses.  w = the entry's two list words, read by every lane from the same address
+// two entries ahead (a warp-wide block of words broadcast by SHFL put the shuffle's latency on the critical path of the
+// short, level-truncated products: 6 % of the stall samples).  Whether nu - nu1 is on the grid is the planner's test:
+// word 0 carries one bit per lane of the box (an integer instruction costs the fp64 stream an issue cycle and the DFMA
+// behind it its operand-reuse hit, tools/dfma_lab: the three-coordinate test in the kernel was 9 of them per entry).
+__device__ __forceinline__ void decode_entry(const LaneGeo& q, const uint2& w, uint32_t& gp, uint32_t& yp) {
+    const uint32_t ei = w.y;
+    const bool ok = (w.x & q.lanebit) != 0;
     const int nat = q.lin - (int)(ei & 0xffff);
     const int gi = ok ? nat : q.zero_rec + ((nat - q.zero_rec) & (RG_ZERO_RECS - 1));
     gp = q.g_base + (uint32_t)(gi * q.rec_bytes);
@@ -264,17 +261,16 @@ __device__ __forceinline__ double2 ldrec(const LaneGeo& q, uint32_t addr) {
 template <int J, int LIM>
 __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
                                             double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& wn,
-                                            uint32_t& gp, uint32_t& yp, int& jm) {
+                                            uint32_t& gp, uint32_t& yp) {
     typedef RecGeom<J> R;
     double gD[2 * R::ND2];
 #pragma unroll
     for (int u = 0; u < R::ND2; ++u) { const double2 t = ldrec(q, gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
     uint32_t gp_n = gp, yp_n = yp;
-    int jm_n = jm;
 #pragma unroll
     for (int k = 0; k < R::NPAD; ++k) {
         const double2 t = yq[k % R::YW];
-        if (k == (R::NP1 > 1 ? 1 : 0)) decode_entry(q, wn, gp_n, yp_n, jm_n);   // after the first block has issued; before the next record is requested (J = 2: NP1 = 1)
+        if (k == (R::NP1 > 1 ? 1 : 0)) decode_entry(q, wn, gp_n, yp_n);   // after the first block has issued; before the next record is requested (J = 2: NP1 = 1)
         if (k + R::YW < R::NPAD) yq[k % R::YW] = ldrec(q, yp + 16 * R::unit(k + R::YW));
         else yq[k % R::YW] = ldrec(q, yp_n + 16 * R::unit(k + R::YW - R::NPAD));
         if (k >= R::NP) continue;   // padding pair
@@ -306,7 +302,7 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
             }
         }
     }
-    gp = gp_n; yp = yp_n; jm = jm_n;
+    gp = gp_n; yp = yp_n;
 }
 
 // One list entry with only the first jm Taylor levels of y present (or, jm = J+2, a caller-supplied generator):
@@ -315,15 +311,14 @@ __device__ __forceinline__ void taylor_full(double (&acc)[J + 1], double (&gO)[2
 template <int J>
 __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO)[2 * RecGeom<J>::NO2],
                                                double2 (&yq)[RecGeom<J>::YW], const LaneGeo& q, const uint2& wn,
-                                               uint32_t& gp, uint32_t& yp, int& jm) {
+                                               uint32_t& gp, uint32_t& yp, const int jm) {
     typedef RecGeom<J> R;
     constexpr int JP = J + 1;
     double gD[2 * R::ND2];
 #pragma unroll
     for (int u = 0; u < R::ND2; ++u) { const double2 t = ldrec(q, gp + 16 * u); gD[2 * u] = t.x; gD[2 * u + 1] = t.y; }
     uint32_t gp_n = gp, yp_n = yp;
-    int jm_n = jm;
-    decode_entry(q, wn, gp_n, yp_n, jm_n);
+    decode_entry(q, wn, gp_n, yp_n);
     // conv(dA y, Omega g): y1[j1] = (j1+1) y[j1+1] is non-zero iff j1+1 < jm
 #pragma unroll
     for (int k = 0; k < R::NP1; ++k) {
@@ -359,11 +354,14 @@ __device__ __forceinline__ void taylor_partial(double (&acc)[J + 1], double (&gO
     }
 #pragma unroll
     for (int k = 0; k < R::YW; ++k) yq[k] = ldrec(q, yp_n + 16 * R::unit(k));
-    gp = gp_n; yp = yp_n; jm = jm_n;
+    gp = gp_n; yp = yp_n;
 }
 
+// One piece of a box's source list.  The planner sorts a list by level class, so a piece is at most three runs (ends
+// e_full <= e_mid <= e_end: complete products, products truncated to LIM_B levels of y, to LIM_A): one counted loop per
+// class.  A caller-supplied generator (schedule kind 1) takes the on-demand product for every entry.
 template <int J>
-__device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, int e_end, double (&acc)[J + 1]) {
+__device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, int e_full, int e_mid, int e_end, double (&acc)[J + 1]) {
     typedef RecGeom<J> R;
     const DevPlan& P = RG_PLAN(c);
     const Sched& S = RG_SCHED(c);
@@ -372,9 +370,8 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     const int lane = threadIdx.x & 31;
     const uint32_t mc = S.lane_coord[box * 32 + lane];
     LaneGeo q;
-    q.v0 = (int)(mc & 0xff) + P.L; q.v1 = (int)((mc >> 8) & 0xff) + P.L; q.v2 = (int)((mc >> 16) & 0xff) + P.L;
-    q.lin = q.v0 * P.stride0 + q.v1 * P.stride1 + q.v2 * P.stride2;
-    q.lim = 2u * (unsigned)P.L;
+    q.lanebit = 1u << lane;
+    q.lin = ((int)(mc & 0xff) + P.L) * P.stride0 + ((int)((mc >> 8) & 0xff) + P.L) * P.stride1 + ((int)((mc >> 16) & 0xff) + P.L) * P.stride2;
     q.zero_rec = P.M;
     q.rec_bytes = P.rec_units * 16;
     q.g_base = (uint32_t)__cvta_generic_to_shared(sm.G);
@@ -386,45 +383,41 @@ __device__ __forceinline__ void conv_piece(const Ctx& c, int box, int e_begin, i
     if (e_begin >= e_end) return;
     // list words of the current entry, the next one (decoded inside the current product) and the one after
     // (in flight); past the end the last entry is read again (harmless, keeps the loop uniform)
-    uint2 wn = entries[min(e_begin + 1, e_end - 1)];
+    const int last = e_end - 1;
+    uint2 wn = entries[min(e_begin + 1, last)];
     uint32_t gp, yp;
-    int jm;
-    decode_entry(q, entries[e_begin], gp, yp, jm);
+    decode_entry(q, entries[e_begin], gp, yp);
 #pragma unroll
     for (int u = 0; u < R::NO2; ++u) { const double2 t = ldrec(q, gp + 16 * (R::ND2 + u)); gO[2 * u] = t.x; gO[2 * u + 1] = t.y; }
 #pragma unroll
     for (int k = 0; k < R::YW; ++k) yq[k] = ldrec(q, yp + 16 * R::unit(k));
-    // The planner sorts a list by level class, so a piece is at most three runs: one tight loop per class (its
-    // exit test uses the class of the NEXT entry, known since the decode early in the product) instead of a
-    // dispatch chain per entry.  The outer loop only repeats if a list were not sorted.
     int i = e_begin;
-    const int last = e_end - 1;
+    if (S.general) {
 #pragma unroll 1
-    while (i < e_end) {
-#pragma unroll 1
-        while (i < e_end && jm > J + 1) {           // caller-supplied y
+        for (; i < e_end; ++i) {
             const uint2 wnn = entries[min(i + 2, last)];
-            taylor_partial<J>(acc, gO, yq, q, wn, gp, yp, jm);
-            wn = wnn; ++i;
+            taylor_partial<J>(acc, gO, yq, q, wn, gp, yp, J + 2);
+            wn = wnn;
         }
+        return;
+    }
 #pragma unroll 1
-        while (i < e_end && jm <= J + 1 && jm > R::LIM_B) {
-            const uint2 wnn = entries[min(i + 2, last)];
-            taylor_full<J, J + 1>(acc, gO, yq, q, wn, gp, yp, jm);
-            wn = wnn; ++i;
-        }
+    for (; i < e_full; ++i) {
+        const uint2 wnn = entries[min(i + 2, last)];
+        taylor_full<J, J + 1>(acc, gO, yq, q, wn, gp, yp);
+        wn = wnn;
+    }
 #pragma unroll 1
-        while (i < e_end && jm <= R::LIM_B && jm > R::LIM_A) {
-            const uint2 wnn = entries[min(i + 2, last)];
-            taylor_full<J, R::LIM_B>(acc, gO, yq, q, wn, gp, yp, jm);
-            wn = wnn; ++i;
-        }
+    for (; i < e_mid; ++i) {
+        const uint2 wnn = entries[min(i + 2, last)];
+        taylor_full<J, R::LIM_B>(acc, gO, yq, q, wn, gp, yp);
+        wn = wnn;
+    }
 #pragma unroll 1
-        while (i < e_end && jm <= R::LIM_A) {
-            const uint2 wnn = entries[min(i + 2, last)];
-            taylor_full<J, R::LIM_A>(acc, gO, yq, q, wn, gp, yp, jm);
-            wn = wnn; ++i;
-        }
+    for (; i < e_end; ++i) {
+        const uint2 wnn = entries[min(i + 2, last)];
+        taylor_full<J, R::LIM_A>(acc, gO, yq, q, wn, gp, yp);
+        wn = wnn;
     }
 }
 
@@ -483,11 +476,7 @@ struct LaneGeoPR {
     const char* gy;           // the Y records: the CTA's global workspace
 };
 
-// next entry: form the two record addresses.  w = the entry's two list words, read by every lane from the same address
-// two entries ahead.  Whether nu - nu1 is on the grid is the planner's test in these kernels: word 0 carries one bit per
-// lane of the box (an integer instruction costs the fp64 stream an issue cycle and the DFMA behind it its operand-reuse
-// hit, tools/dfma_lab; the three-coordinate test was 9 of them per entry: bracket of config 5 1.120 M -> 1.067 M clocks.
-// The shared-memory kernels keep the test: there ptxas turned the shorter decode into a slower schedule, +1.9 %).
+// next entry: form the two record addresses (word 0 of an entry: the lanes whose nu - nu1 is on the grid; decode_entry).
 // An out-of-range lane gathers the zero record congruent (mod 8) to the record it would have read.
 __device__ __forceinline__ void decode_entry_pr(const LaneGeoPR& q, const uint2& w, uint32_t& gp, uint32_t& yp, int& nat_out) {
     const uint32_t ei = w.y;
@@ -765,7 +754,8 @@ __device__ RG_CONV_ATTR void conv_all(Ctx& c) {
                         for (int j = 0; j < JP; ++j) acc[j] = om * S1[j] - (double)(j + 1) * S2[j];
                     }
                 } else {
-                    conv_piece<J>(c, p.x, p.y, p.z, acc);
+                    const int2 r = S.piece_runs[((size_t)st * S.n_warps + pw) * S.maxp + q];
+                    conv_piece<J>(c, p.x, p.y, r.x, r.y, p.z, acc);
                 }
                 if (lane == 0) {
                     if (st) while (vctl[nb_all] < need0) {}

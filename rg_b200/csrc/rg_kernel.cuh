@@ -55,7 +55,7 @@ __device__ __forceinline__ int fetch_item(const Job& job) { return atomicAdd(job
 // Threads and registers.  Orders J >= 8 on the shared-memory path run 8 warps of 255 registers, one CTA per SM: with the
 // 168 registers of 12 warps ptxas folds the two halves of the gathered record and the next entry's operands onto the same
 // registers, so their loads can only be issued a few cycles before the data is needed (11 % of the hot loop's stall
-// samples were shared-memory scoreboard waits); with 253 registers the loads sit half a list entry ahead and two warps
+// samples were shared-memory scoreboard waits); with 255 registers the loads sit half a list entry ahead and two warps
 // per sub-partition keep the fp64 pipe busier than three did (L = J = 10, uniform batch: bracket 114.2 k -> 107.2 k
 // clocks, kernel -4.5 %; 4 warps: +17 %).  BIG kernels keep 12 warps x 168: their y records come through L1 and need the
 // extra warps to cover it (8 warps: bracket +15 %).  Small orders: 8 warps x 128 registers, two CTAs per SM.

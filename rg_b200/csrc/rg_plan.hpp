@@ -110,8 +110,7 @@ struct Schedule {
     std::vector<int32_t> piece_runs;   // [n_stages][NW*maxp][2]: end of the piece's run of complete products, end of its LIM_B run
     bool general = false;              // caller-supplied generator (dense): every entry takes the general product
     bool prule = false;                // costs counted for the product-rule form of the bracket (BIG kernels)
-    std::vector<uint32_t> entries;     // [n*2]: {biased coords of nu1 (8 bits each) | jm<<24 -- prule: lanes of the piece's box whose nu - nu1 is
-                                       // on the grid (bit l = lane l), centred index of nu1 | rec<<16}
+    std::vector<uint32_t> entries;     // [n*2]: {lanes of the piece's box whose nu - nu1 is on the grid (bit l = lane l), centred index of nu1 | rec<<16}
     std::vector<uint8_t> entry_jm;     // [n]: Taylor levels of y present at the entry's nu1 (J+2: caller-supplied generator)
     std::vector<int32_t> supp_rec;     // [M] record index of centred nu1, -1 if not in support
     std::vector<uint8_t> jm;           // [M] 1 + highest I^- level (0 = not in support)
@@ -364,11 +363,9 @@ inline Schedule make_schedule_impl(const Geometry& g, const std::vector<uint16_t
                     while (k < lists[b].size()) {
                         const int c1 = lists[b][k];
                         if (w < w1 - 1 && acc * NWc >= gtotal * (int64_t)(w - w0 + 1) && (int)s.entries.size() / 2 > pc.begin) break;
-                        // word0: biased coords of nu1 (the kernel's range test) | jm<<24 -- product-rule form (BIG kernels):
-                        // the lanes in range (the test is the planner's; the level class is in the piece's run ends);
-                        // word1: centred linear index | record<<16
-                        int v1[4]; g.coords(c1, v1);
-                        s.entries.push_back(prule ? valid_mask(order, b, c1) : (g.pack(v1) | ((uint32_t)s.jm[c1] << 24)));
+                        // word0: the lanes of the box in range for nu1 (the range test is the planner's, not the kernel's; the
+                        // level class of an entry is in the piece's run ends); word1: centred linear index | record<<16
+                        s.entries.push_back(valid_mask(order, b, c1));
                         s.entries.push_back((uint32_t)c1 | ((uint32_t)s.supp_rec[c1] << 16));
                         s.entry_jm.push_back(s.jm[c1]);
                         acc += wcost_of(c1); wcost[w] += wcost_of(c1);

@@ -103,7 +103,7 @@ def fetch_schedule(c, mode):
     im_c = np.roll(c.Iminus, c.dim * (c.L,), axis=tuple(range(1, c.dim + 1))).reshape(c.J + 1, -1)
     jm = np.where(im_c.any(axis=0), c.J + 1 - np.argmax(im_c[::-1], axis=0), 0)
     out["jm"] = np.full(M, c.J + 2) if mode == 1 else jm
-    # word 0 of an entry: biased coords of nu1 | jm<<24, or -- plans of the product-rule form (BIG kernels) -- the range mask
+    # word 0 of an entry: the range mask of the box's lanes; product-rule plans (BIG kernels) are flagged
     runs, nslots, pr = ctypes.POINTER(ctypes.c_int32)(), ctypes.c_int32(), ctypes.c_int32()
     _lib.check(L_.rg_debug_piece_runs(c.dim, c.L, c.J, im.ctypes.data, int(mode), ctypes.byref(runs), ctypes.byref(nslots), ctypes.byref(pr)))
     L_.rg_debug_free(runs)
@@ -152,15 +152,13 @@ def replay(c, sched, y1, y2, g, Omega_nu):
                 nu1 = nu_of_rec[rec]
                 assert (int(ent[1]) & 0xffff) == nu1
                 jm = int(sched["jm"][nu1])
-                if not sched["prule"]:
-                    assert [(mask >> (8 * d)) & 0xff for d in range(dim)] == list(coords[nu1]) and mask >> 24 == jm
                 for l, nu in enumerate(lanes):
                     if nu < 0:
-                        assert not (sched["prule"] and (mask >> l) & 1), "an idle lane is never in range"
+                        assert not (mask >> l) & 1, "an idle lane is never in range"
                         continue
                     u = coords[nu] - coords[nu1] + L
                     ok = bool(((u >= 0) & (u <= 2 * L)).all())
-                    assert not sched["prule"] or ok == bool((mask >> l) & 1), "word 0 of an entry is the box's range mask"
+                    assert ok == bool((mask >> l) & 1), "word 0 of an entry is the box's range mask"
                     gi = int((u * strides).sum()) if ok else M
                     for j1 in range(J + 1):
                         if j1 + 1 < jm:                  # y1[j1] = (j1+1) y[j1+1]; jm = J+2 keeps a caller's y1[J]
@@ -273,7 +271,7 @@ def test_schedule_geometry_config5():
             have = set()
             for _, b, e in seen.get(box, []):
                 have |= set((s["entries"][b:e, 1] & 0xffff).astype(int))
-                # product-rule plans: word 0 of an entry is the range mask of this box's 32 lanes (the kernel has no test)
+                # word 0 of an entry is the range mask of this box's 32 lanes (the kernel has no test of its own)
                 assert s["prule"]
                 all_l = lanes[box * 32:(box + 1) * 32]
                 act = all_l >= 0
@@ -337,8 +335,8 @@ def test_sass_tune_round_trip(tmp_path):
 def test_hot_loop_canary():
     """ptxas allocates the hot loop of conv_all together with the rest of the kernel: an edit anywhere in rg_device.cuh can
     change its schedule by several per cent either way (the epilogue's chunk size moved the bracket from 107 k to
-    117 k clocks).  Static canary on the built L=J=10 object: the complete-product loop body has 130 DFMAs, no more than 60
-    other instructions, no spills, a stall-count sum below 300 cycles and -- in the linked, retuned library -- at least 64
+    117 k clocks).  Static canary on the built L=J=10 object: the complete-product loop body has 130 DFMAs, no more than 45
+    other instructions, no spills, a stall-count sum below 305 cycles and -- in the linked, retuned library -- at least 78
     adjacent operand-reuse hits.  A failure here means: measure before committing."""
     import shutil
     import sys
@@ -359,10 +357,10 @@ def test_hot_loop_canary():
                 hits += 1
         return ins, hits
     ins, hits = main_block(_lib.SO_PATH)
-    assert len(ins) - 130 <= 60, len(ins)
-    assert sum(max(x.stall, 1) for x in ins) < 300
+    assert len(ins) - 130 <= 45, len(ins)
+    assert sum(max(x.stall, 1) for x in ins) < 305
     assert not any(x.op.startswith(("LDL", "STL")) for x in ins), "the hot loop spills"
-    assert hits >= 64, hits
+    assert hits >= 78, hits
 
 
 def test_sass_sched_study_tool_keeps_its_hazard_rules(tmp_path):

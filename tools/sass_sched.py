@@ -133,11 +133,24 @@ def parse(addr, text, lo, hi):
         return x
     w = DST_WIDTH[x.op]
     d = regs_of(ops[0])
-    if len(d) != 1 or d[0][0] not in ('R', 'UR'):
+    first_src = 1
+    if x.op == 'LOP3.LUT' and len(d) == 1 and d[0][0] == 'P':
+        # LOP3.LUT P1, RZ|Rd, Ra, Rb, Rc, lut, !PT : a predicate result next to the (possibly discarded) register result
+        writes.add(('P', d[0][1]))
+        d = regs_of(ops[1])
+        first_src = 2
+        if not d and ops[1] != 'RZ':
+            x.reads = x.writes = None
+            return x
+    if d and (len(d) != 1 or d[0][0] not in ('R', 'UR')):
         x.reads = x.writes = None
         return x
-    writes |= expand(d[0][0], d[0][1], w)
-    for i, o in enumerate(ops[1:], 1):
+    if not d and first_src == 1:
+        x.reads = x.writes = None
+        return x
+    if d:
+        writes |= expand(d[0][0], d[0][1], w)
+    for i, o in enumerate(ops[first_src:], first_src):
         for k, n, w64 in regs_of(o):
             wide = 2 if (w64 or (x.op.startswith('IMAD.WIDE') and i == len(ops) - 1) or o.startswith('desc[') and k == 'UR') else 1
             reads |= expand(k, n, wide)
